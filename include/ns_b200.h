@@ -1,0 +1,177 @@
+/*
+ * ns_b200.h — C ABI of the B200 error-model library (libns_b200.so).
+ *
+ * This is the drop-in boundary for needlestack's per-site hot path: plain C, plain
+ * pointers and sizes, no R / torch / C++ types.  Each entry point names the reference
+ * interface it replaces (paths under the needlestack tree, bin/...).
+ *
+ *   reference today (interpreted R)                      this library
+ *   ------------------------------------------------     -----------------------------------
+ *   glmrob.nb(y, x, ...)        bin/glm_rob_nb.r:16-228   ns_glmrob_nb(), ns_call_units(plain=1)
+ *   per-allele SNV body         bin/needlestack.r:321-413 ns_call_snv(), ns_call_snv_device()
+ *   per-allele DEL / INS body   bin/needlestack.r:461-567,
+ *                               :624-730                  ns_call_units(is_indel=1)
+ *   annotate_vcf.r DP/AD loop   bin/annotate_vcf.r:57-69  ns_call_units()
+ *   toQvalueN / toQvalueT       bin/needlestack.r:242-252 (fused into the calls above)
+ *   SOR / common_annot          bin/needlestack.r:206-239 (fused)
+ *
+ * One "unit" = one (position, candidate allele) = one glmrob.nb() call of the reference.
+ * All count inputs are int32.  All entry points are synchronous: when they return, every
+ * requested output is in the caller's host memory.  Return 0 on success, a negative
+ * NS_ERR_* otherwise (message via ns_last_error).  The library has no CPU path: without a
+ * CUDA device ns_create() fails.
+ */
+#ifndef NS_B200_H
+#define NS_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NS_ABI_VERSION 1
+
+/* ---- error codes ---------------------------------------------------------------- */
+#define NS_OK 0
+#define NS_ERR_CUDA (-1)          /* a CUDA runtime call failed */
+#define NS_ERR_ARG (-2)           /* bad argument (null pointer, n < 1, unsupported option) */
+#define NS_ERR_EMIT_OVERFLOW (-3) /* more emitted units than out->emit_cap; out->n_emitted = needed */
+#define NS_ERR_NOMEM (-4)
+
+/* ---- unit flag word (out->flags[u]) ---------------------------------------------- */
+#define NS_F_GATED 0x001u      /* glm_rob_nb.r:38-49 returned the NA result */
+#define NS_F_EXTRA_ROB 0x002u  /* extra-robust pre-filter removed samples (glm_rob_nb.r:22-36) */
+#define NS_F_REF_INV 0x004u    /* regression on the REF counts (needlestack.r:330-337) */
+#define NS_F_SIG_AT_MIN 0x008u /* last uniroot() failed -> sigma = minsig (glm_rob_nb.r:175-178) */
+#define NS_F_MAXIT 0x010u      /* outer loop stopped by maxit */
+#define NS_F_QUAD_ERROR 0x020u /* integrate() error inside the IRLS loop: the reference would stop() */
+#define NS_F_NAN_ROWS 0x040u   /* NaN weights/responses dropped in the WLS step */
+#define NS_F_GATE1 0x080u      /* needlestack.r:381 passed (strand-bias annotations valid) */
+#define NS_F_GATE2 0x100u      /* needlestack.r:387 passed (the reference writes a VCF line) */
+#define NS_F_SKIPPED 0x200u    /* REF not in A,T,C,G: position skipped (needlestack.r:319) */
+#define NS_F_QUAD_OVERFLOW 0x400u /* quadrature needed more than the on-chip interval list */
+
+/* genotype codes (needlestack.r:403-409) and somatic status (needlestack.r:342-373) */
+enum { NS_GT_00 = 0, NS_GT_01 = 1, NS_GT_11 = 2, NS_GT_MISSING = 3 };
+enum {
+    NS_ST_NONE = 0, /* "." */
+    NS_ST_SOMATIC = 1,
+    NS_ST_GERMLINE_CONFIRMED = 2,
+    NS_ST_GERMLINE_UNCONFIRMED = 3,
+    NS_ST_GERMLINE_UNCONFIRMABLE = 4,
+    NS_ST_UNKNOWN = 5,
+    NS_ST_POSSIBLE_CONTAMINATION = 6
+};
+
+/* which units get per-sample rows in the emitted planes */
+enum {
+    NS_EMIT_CALLS = 0,  /* units the reference writes to the VCF (gate 2) */
+    NS_EMIT_FITTED = 1, /* every unit that was fitted (not gated) */
+    NS_EMIT_ALL = 2     /* every unit that was not skipped (gated ones: p=q=1, GQ=0) */
+};
+
+/* ---- parameters ------------------------------------------------------------------ */
+typedef struct ns_params {
+    /* glmrob.nb() arguments, bin/glm_rob_nb.r:16-18 (maxmu is ignored there, :20) */
+    double c_tukey_beta, c_tukey_sig, minsig, maxsig, minmu, sig_prec, tol;
+    double min_coverage, min_reads, min_af;
+    double min_af_extra_rob, min_prop_extra_rob, max_prop_extra_rob;
+    int32_t maxit, maxit_sig, n_ai_sig_tukey, size_min, extra_rob;
+    /* caller level, bin/needlestack.r:64-92 */
+    int32_t SB_type; /* 0 SOR, 1 RVSB, 2 FS */
+    int32_t output_all_SNVs;
+    int32_t is_tn; /* a pairs file was supplied (needlestack.r:162-185) */
+    double GQ_threshold, SB_threshold_SNV, SB_threshold_indel;
+    double sigma_normal; /* --sigma_normal, toQvalueN */
+    double afmin_power;  /* -1: unset */
+    /* tumour/normal index sets, 0-based sample indices, HOST pointers (copied per call) */
+    int32_t n_pairs, n_only_t, n_only_n;
+    int32_t emit_mode; /* NS_EMIT_* */
+    const int32_t *tindex, *nindex, *only_t, *only_n;
+    const uint8_t *role; /* internal (device side); ignored on input */
+} ns_params;
+
+/* glmrob.nb()'s own defaults (bin/glm_rob_nb.r:16-18); caller fields zeroed */
+void ns_params_glm_default(ns_params *p);
+/* needlestack.r's defaults (bin/needlestack.r:64-92) on top of the above */
+void ns_params_caller_default(ns_params *p);
+
+/* ---- outputs (all caller-allocated HOST memory; any pointer may be NULL = not wanted) */
+typedef struct ns_out {
+    /* per unit, length n_units */
+    double *sigma, *slope; /* NaN when gated (R: NA) */
+    double *max_gq;        /* max(reg_res$GQ): the VCF QUAL column */
+    uint32_t *flags;       /* NS_F_* */
+    uint32_t *iters;       /* n_outer | n_irls << 8 | n_objective_evals << 18 */
+    int32_t *emit_index;   /* row in the emitted planes, or -1 */
+    /* emitted rows, in increasing unit order */
+    int64_t emit_cap;  /* in: rows available in the planes below */
+    int64_t n_emitted; /* out */
+    int64_t *emit_unit; /* [emit_cap] unit id of each row */
+    double *pvalue, *qvalue, *gq, *qval_minaf, *sor, *rvsb, *fs; /* [emit_cap][n] */
+    uint8_t *gt, *status;                                        /* [emit_cap][n] */
+    double *pooled; /* [emit_cap][8]: all_sor, all_rvsb, FisherStrand_all, sum Rp, Rm, Vp, Vm, all_DP */
+    /* batch counters (out) */
+    int64_t n_fitted, n_gated, n_skipped;
+    uint64_t n_seed, n_lattice, n_quad; /* work counters of SURVEY.md section 8(d) */
+} ns_out;
+
+/* per-call device timings of the last ns_call_* on this context, milliseconds */
+typedef struct ns_timings {
+    double h2d_ms, gate_ms, fit_ms, post_ms, pack_ms, d2h_ms, total_ms;
+    int64_t kernel_launches;
+} ns_timings;
+
+typedef struct ns_ctx ns_ctx;
+
+/* ---- life cycle ------------------------------------------------------------------ */
+int ns_abi_version(void);
+/* one context per GPU and host thread; device = CUDA ordinal */
+ns_ctx *ns_create(int device, char *err, size_t errlen);
+void ns_destroy(ns_ctx *ctx);
+const char *ns_last_error(ns_ctx *ctx);
+/* run the context's kernels on a caller-owned CUDA stream (cudaStream_t), 0 = own stream */
+int ns_set_stream(ns_ctx *ctx, void *cuda_stream);
+/* page-locked host buffers for the columnar loader */
+void *ns_alloc_pinned(size_t bytes);
+void ns_free_pinned(void *p);
+int ns_get_timings(ns_ctx *ctx, ns_timings *t);
+
+/* ---- the hot path ---------------------------------------------------------------- */
+/*
+ * SNV units of P positions.  counts: int32 [P][9][n], planes in the table's column order
+ * depth, A, T, C, G, a, t, c, g (bin/needlestack.r:188-198); ref: uint8 [P], 0..3 = A,T,C,G,
+ * anything else = position skipped (:319).  Unit u = 3*p + k is the k-th allele of
+ * setdiff(c("A","T","C","G"), ref) (:321).  Replaces the body of needlestack.r:321-413
+ * up to (not including) the text of the VCF line.
+ */
+int ns_call_snv(ns_ctx *ctx, const ns_params *prm, int n_samples, int64_t n_positions,
+                const uint8_t *ref, const int32_t *counts, ns_out *out);
+/* same, inputs already resident on the context's device */
+int ns_call_snv_device(ns_ctx *ctx, const ns_params *prm, int n_samples, int64_t n_positions,
+                       const uint8_t *d_ref, const int32_t *d_counts, ns_out *out);
+/*
+ * Explicit units: int32 rows [n_units][n] of depth, alt fwd, alt rev, ref fwd, ref rev
+ * (vm, rp, rm may be NULL = zeros).  is_indel: uint8 [n_units] or NULL.  plain != 0 runs
+ * glmrob.nb(y = vp (+vm), x = dp) without the caller's ref-inversion test.
+ * Replaces needlestack.r:461-567 (DEL), :624-730 (INS), annotate_vcf.r:57-69.
+ */
+int ns_call_units(ns_ctx *ctx, const ns_params *prm, int n_samples, int64_t n_units,
+                  const int32_t *dp, const int32_t *vp, const int32_t *vm, const int32_t *rp,
+                  const int32_t *rm, const uint8_t *is_indel, int plain, ns_out *out);
+/*
+ * One glmrob.nb(y, x, ...) call (bin/glm_rob_nb.r:16): outputs are the fields of its
+ * result list: coef = (sigma, slope), pvalues, qvalues, GQ (length n), extra_rob.
+ */
+int ns_glmrob_nb(ns_ctx *ctx, const ns_params *prm, int n_samples, const int32_t *y,
+                 const int32_t *x, double *sigma, double *slope, double *pvalues, double *qvalues,
+                 double *gq, int32_t *extra_rob, uint32_t *flags);
+
+/* FP64 FMA peak of the context's device, TFLOP/s (the denominator of the fit roofline) */
+int ns_measure_fp64_peak(ns_ctx *ctx, double *tflops);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

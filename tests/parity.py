@@ -1,0 +1,139 @@
+"""Shared parity checker: compares a result set (CUDA path or its serial emulation) with the
+CPU oracle on the same units.  Tolerances follow BASELINE.json's north_star: candidate
+selection, gates, genotypes and status bit-exact; sigma, slope relative 1e-6; p/q-values and
+Phred values abs(d) <= 1e-6*max(1, |value|)."""
+import numpy as np
+
+from needlestack_b200 import _abi
+
+TOL = 1e-6
+
+
+def snv_unit_rows(ref, counts, u):
+    """rows (dp, vp, vm, rp, rm) of SNV unit u = 3p+k from counts [P][9][n]"""
+    p, k = divmod(u, 3)
+    r = int(ref[p])
+    alts = [b for b in range(4) if b != r]
+    a = alts[k]
+    c = counts[p]
+    return c[0], c[1 + a], c[5 + a], c[1 + r], c[5 + r]
+
+
+def emul_snv_batch(emul, ref, counts, prm, pairs=None):
+    P, _, n = counts.shape
+    U = 3 * P
+    keys_d = ("pvalue", "qvalue", "gq", "qval_minaf", "sor", "rvsb", "fs")
+    out = {k: np.full((U, n), np.nan) for k in keys_d}
+    out["gt"] = np.zeros((U, n), dtype=np.uint8)
+    out["status"] = np.zeros((U, n), dtype=np.uint8)
+    out["pooled"] = np.zeros((U, 8))
+    for k in ("sigma", "slope", "max_gq"):
+        out[k] = np.full(U, np.nan)
+    for k in ("flags", "n_outer", "n_irls", "n_obj"):
+        out[k] = np.zeros(U, dtype=np.int64)
+    for u in range(U):
+        if ref[u // 3] > 3:
+            out["flags"][u] = _abi.NS_F_SKIPPED | _abi.NS_F_GATED
+            continue
+        E = emul.call_unit(*snv_unit_rows(ref, counts, u), prm, pairs=pairs)
+        for k in keys_d + ("gt", "status", "pooled"):
+            out[k][u] = E[k]
+        for k in ("sigma", "slope", "max_gq", "flags", "n_outer", "n_irls", "n_obj"):
+            out[k][u] = E[k]
+    return out
+
+
+def _rel(a, b):
+    return np.abs(a - b) / np.maximum(1.0, np.abs(b))
+
+
+def _close(a, b, tol):
+    """elementwise: equal NaN pattern, equal infinities, |a-b| <= tol*max(1,|b|)"""
+    a = np.asarray(a, dtype=float)
+    b = np.asarray(b, dtype=float)
+    nan_ok = np.isnan(a) == np.isnan(b)
+    inf = np.isinf(a) | np.isinf(b)
+    inf_ok = np.where(inf, a == b, True)
+    fin = ~(np.isnan(a) | np.isnan(b) | inf)
+    d = np.zeros_like(a)
+    d[fin] = _rel(a[fin], b[fin])
+    return nan_ok & inf_ok & (d <= tol), d
+
+
+def compare(O, R, units=None, tol=TOL, gq_thr=50.0, label=""):
+    """O: oracle dict (tests/orc.call_snv_batch layout), R: result dict with the same per-unit
+    arrays plus 'flags'.  Returns a report dict; raises AssertionError on any mismatch that is
+    not a documented near-threshold flip."""
+    U = len(O["sigma"])
+    units = range(U) if units is None else units
+    rep = dict(n_units=0, n_fitted=0, max_rel_sigma=0.0, max_rel_slope=0.0, max_d_gq=0.0, max_d_qval=0.0,
+               max_d_p=0.0, max_d_sb=0.0, gt_mismatch=0, status_mismatch=0, gate_mismatch=0, iter_mismatch=0,
+               near_threshold=0, bad=[])
+    for u in units:
+        rep["n_units"] += 1
+        fl = int(R["flags"][u])
+        gated_r = bool(fl & _abi.NS_F_GATED)
+        if bool(O["gated"][u]) != gated_r or bool(O["ref_inv"][u]) != bool(fl & _abi.NS_F_REF_INV) or \
+                bool(O["extra_rob"][u]) != bool(fl & _abi.NS_F_EXTRA_ROB):
+            rep["gate_mismatch"] += 1
+            rep["bad"].append((u, "gate/ref_inv/extra_rob flags"))
+            continue
+        if fl & _abi.NS_F_SKIPPED:
+            continue
+        if not gated_r:
+            rep["n_fitted"] += 1
+            ds = abs(R["sigma"][u] - O["sigma"][u]) / abs(O["sigma"][u])
+            dl = abs(R["slope"][u] - O["slope"][u]) / abs(O["slope"][u])
+            rep["max_rel_sigma"] = max(rep["max_rel_sigma"], ds)
+            rep["max_rel_slope"] = max(rep["max_rel_slope"], dl)
+            if not (ds <= tol and dl <= tol):
+                rep["bad"].append((u, f"sigma/slope rel {ds:.3g}/{dl:.3g}"))
+                continue
+            if "n_outer" in R and R["n_outer"][u] != O["n_outer"][u]:
+                rep["iter_mismatch"] += 1
+        else:
+            if not (np.isnan(R["sigma"][u]) and np.isnan(R["slope"][u])):
+                rep["bad"].append((u, "gated unit with non-NA coef"))
+        for key, fld in (("pvalue", "max_d_p"), ("qvalue", "max_d_p"), ("gq", "max_d_gq"),
+                         ("qval_minaf", "max_d_qval")):
+            ok, d = _close(R[key][u], O[key][u], tol)
+            rep[fld] = max(rep[fld], float(d.max()) if d.size else 0.0)
+            if not ok.all():
+                rep["bad"].append((u, f"{key} max d {d.max():.3g} (nan/inf pattern ok: "
+                                      f"{bool((np.isnan(R[key][u]) == np.isnan(O[key][u])).all())})"))
+        g1_o, g1_r = bool(O["gate1"][u]), bool(fl & _abi.NS_F_GATE1)
+        g2_o, g2_r = bool(O["gate2"][u]), bool(fl & _abi.NS_F_GATE2)
+        near = np.any(np.abs(O["gq"][u] - gq_thr) < 1e-5) or np.any(np.abs(O["qval_minaf"][u] - gq_thr) < 1e-5)
+        if g1_o != g1_r or g2_o != g2_r:
+            if near:
+                rep["near_threshold"] += 1
+                continue
+            rep["gate_mismatch"] += 1
+            rep["bad"].append((u, "gate1/gate2"))
+            continue
+        if not np.array_equal(R["status"][u], O["status"][u]):
+            if near:
+                rep["near_threshold"] += 1
+            else:
+                rep["status_mismatch"] += 1
+                rep["bad"].append((u, "status"))
+        if g1_o:
+            for key in ("sor", "rvsb", "fs"):
+                ok, d = _close(R[key][u], O[key][u], tol)
+                rep["max_d_sb"] = max(rep["max_d_sb"], float(d.max()))
+                if not ok.all():
+                    rep["bad"].append((u, f"{key} max d {d.max():.3g}"))
+            ok, d = _close(R["pooled"][u], O["pooled"][u], tol)
+            if not ok.all():
+                rep["bad"].append((u, f"pooled max d {d.max():.3g}"))
+            if not np.array_equal(R["gt"][u], O["gt"][u]):
+                if near:
+                    rep["near_threshold"] += 1
+                else:
+                    rep["gt_mismatch"] += 1
+                    rep["bad"].append((u, "genotype"))
+            ok, d = _close(R["max_gq"][u], O["max_gq"][u], tol)
+            if not ok.all():
+                rep["bad"].append((u, "max_gq"))
+    assert not rep["bad"], f"{label}: {len(rep['bad'])} mismatching units, first: {rep['bad'][:5]}; report {rep}"
+    return rep
