@@ -1,0 +1,414 @@
+#!/usr/bin/env python
+"""bench.py — site-alleles fitted / s (robust NB + p/q-values) on B200, with the CPU path beside it.
+
+One "step" = one pass of the hot path (gate -> robust NB fit -> p/q/GQ, Holm power q-values, status,
+strand bias, genotypes) over one synthetic readcount batch of the BASELINE.json configuration
+configs[1]: 100 samples x 1 Mb of targets at ~100X (C2).  Region-sharded weak scaling: every rank
+owns its own 1 Mb region (different seed), no data-path collective.
+
+    value   device-resident: the count planes are already in HBM when the timed region starts
+    e2e     through the public API with HOST (pinned) buffers: H2D of the planes and D2H of the
+            results inside the timed region
+    roofline      the fit kernel (k_fit) against the measured FP64 FMA peak of the same GPU
+    roofline_gate the streaming gate kernel (k_gate) against the measured HBM copy bandwidth
+    cpu_baseline  the CPU oracle (C restatement of the R reference; R itself is not installable
+                  here) on a bounded sample of the same batch, all host cores
+
+`--impl reference` times that CPU oracle alone (the reference arm of this tier).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+METRIC = "site-alleles fitted/sec (robust NB + p/q-values)"
+UNIT = "site-alleles/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--config", default="C2")
+    ap.add_argument("--positions", type=int, default=0, help="positions per rank per step (0 = the config's P)")
+    ap.add_argument("--samples", type=int, default=0)
+    ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target CPU-baseline sample duration")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--p-germline", type=float, default=1e-4)
+    ap.add_argument("--dump-cycles", default="")
+    return ap.parse_args()
+
+
+# ---- synthetic batch on the GPU (same model as needlestack_b200.synth, torch RNG) ------------
+def generate_torch(cfg, P, seed, device, p_germline=1e-4):
+    import torch
+    n = cfg.n
+    g = torch.Generator(device=device)
+    g.manual_seed(int(seed))
+    f32 = torch.float32
+
+    def rnd(*shape):
+        return torch.rand(*shape, generator=g, device=device, dtype=f32)
+
+    def gamma(shape_t):
+        return torch._standard_gamma(shape_t, generator=g)
+
+    scale = torch.exp(0.25 * torch.randn(n, generator=g, device=device, dtype=f32))
+    mean_dp = cfg.depth * scale[None, :]
+    lam = gamma(torch.full((P, n), 20.0, device=device, dtype=f32)) * (mean_dp / 20.0)
+    DP = torch.poisson(lam, generator=g)
+    del lam
+    ref = torch.randint(0, 4, (P,), generator=g, device=device)
+    room = DP.clone()
+    ys = []
+    var_pos = torch.nonzero(rnd(P) < 1e-3).flatten()
+    var_k = torch.randint(0, 3, (len(var_pos),), generator=g, device=device)
+    germ_pos = torch.nonzero(rnd(P) < p_germline).flatten()
+    germ_k = torch.randint(0, 3, (len(germ_pos),), generator=g, device=device)
+    for k in range(3):
+        e = 10.0 ** (cfg.e_lo + (cfg.e_hi - cfg.e_lo) * rnd(P, 1))
+        sg = 10.0 ** (cfg.s_lo + (cfg.s_hi - cfg.s_lo) * rnd(P, 1))
+        shape = (1.0 / sg).expand(P, n).contiguous()
+        lam_k = gamma(shape) * (e * DP * sg)
+        y = torch.poisson(lam_k, generator=g)
+        del lam_k, shape
+        # planted variants in a few samples, common germline sites in ~30 %
+        vp = var_pos[var_k == k]
+        if len(vp):
+            carriers = rnd(len(vp), n) < (1.5 / n)
+            forced = torch.randint(0, n, (len(vp),), generator=g, device=device)
+            carriers[torch.arange(len(vp), device=device), forced] = True
+            if cfg.af_log:
+                af = 10.0 ** (cfg.af_lo + (cfg.af_hi - cfg.af_lo) * rnd(len(vp), n))
+            else:
+                af = cfg.af_lo + (cfg.af_hi - cfg.af_lo) * rnd(len(vp), n)
+            add = torch.binomial(DP[vp], af * carriers, generator=g)
+            y[vp] += add
+        gp = germ_pos[germ_k == k]
+        if len(gp):
+            carriers = rnd(len(gp), n) < 0.3
+            af = torch.where(rnd(len(gp), n) < 0.5, 0.5, 1.0)
+            y[gp] += torch.binomial(DP[gp], af * carriers, generator=g)
+        y = torch.minimum(y, room)
+        room -= y
+        ys.append(y)
+    counts = torch.zeros((P, 9, n), device=device, dtype=torch.int32)
+    counts[:, 0, :] = DP.to(torch.int32)
+    pidx = torch.arange(P, device=device)
+    alts = torch.tensor([[b for b in range(4) if b != r] for r in range(4)], device=device)
+    half = torch.full((1,), 0.5, device=device, dtype=f32)
+    for k in range(3):
+        b = alts[ref, k]
+        fwd = torch.binomial(ys[k], half.expand_as(ys[k]), generator=g)
+        counts[pidx, 1 + b, :] = fwd.to(torch.int32)
+        counts[pidx, 5 + b, :] = (ys[k] - fwd).to(torch.int32)
+    rf = torch.binomial(room, half.expand_as(room), generator=g)
+    counts[pidx, 1 + ref, :] = rf.to(torch.int32)
+    counts[pidx, 5 + ref, :] = (room - rf).to(torch.int32)
+    return ref.to(torch.uint8).contiguous(), counts.contiguous()
+
+
+# ---- clocks during the timed region ---------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.Q}",
+                                       "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.f,
+                                      stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        for line in self.f.read().splitlines():
+            c = [x.strip() for x in line.split(",")]
+            if len(c) < 9:
+                continue
+            try:
+                sm.append(float(c[1]))
+                mx.append(float(c[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, c[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        try:
+            os.unlink(self.f.name)
+        except OSError:
+            pass
+        if sm:
+            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons),
+                       samples=len(sm))
+        return out
+
+
+# ---- the CPU arm --------------------------------------------------------------------------
+def cpu_oracle_rate(ref_np, counts_np, n_threads, target_s, prm_kw):
+    """fitted site-alleles / s of the CPU oracle on the first positions of the batch (bounded sample)."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import orc
+    orc.lib()
+    prm = orc.call_params(**prm_kw)
+
+    def run(Ps):
+        c = np.ascontiguousarray(counts_np[:Ps].transpose(1, 0, 2))
+        t = time.perf_counter()
+        O = orc.call_snv_batch(ref_np[:Ps], c, prm, n_threads=n_threads)
+        dt = time.perf_counter() - t
+        return dt, int((O["gated"] == 0).sum())
+
+    Pmax = len(ref_np)
+    Ps = min(Pmax, 64 * n_threads)
+    dt, nf = run(Ps)
+    if dt < target_s / 3 and Ps < Pmax:
+        Ps2 = int(min(Pmax, max(Ps, Ps * target_s / max(dt, 1e-3))))
+        Ps2 -= Ps2 % n_threads
+        if Ps2 > Ps:
+            Ps = Ps2
+            dt, nf = run(Ps)
+    return dict(value=nf / dt, fitted=nf, seconds=dt, positions=Ps)
+
+
+def main():
+    a = parse()
+    from needlestack_b200 import synth
+    cfg = synth.CONFIGS[a.config]
+    if a.samples:
+        cfg = synth.Config(**{**cfg.__dict__, "n": a.samples})
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    P = a.positions or cfg.P
+    n = cfg.n
+    workload = f"{a.config}: {n} samples x {P} positions/GPU at ~{cfg.depth:g}X, SNV alleles (3 per position)"
+    config = {"workload": workload, "samples": n, "positions_per_gpu": P, "depth": cfg.depth,
+              "parallelism": f"region-sharded x{world}", "l2": "inputs (%.2f GB/GPU) larger than L2" %
+              (P * 9 * n * 4 / 1e9), "params": "needlestack.r defaults (min_coverage 30, min_reads 3, GQ 50, SOR 100)"}
+    ncores = os.cpu_count() or 1
+
+    if a.impl == "reference":
+        # the reference arm of this tier: the CPU restatement of the R path (R is not installable
+        # here), all host cores, bounded sample of the same workload per step
+        if rank != 0:
+            return 0
+        Ps = min(P, 4096)
+        ref_np, counts_np = synth.generate(cfg, P=Ps, seed=cfg.seed)
+        rates = []
+        t_all = time.perf_counter()
+        per = max(2.0, min(20.0, 120.0 / max(1, a.steps + a.warmup)))
+        res = None
+        for i in range(a.warmup + a.steps):
+            res = cpu_oracle_rate(ref_np, counts_np, ncores, per, {})
+            if i >= a.warmup:
+                rates.append(res)
+        fitted = sum(r["fitted"] for r in rates)
+        secs = sum(r["seconds"] for r in rates)
+        val = fitted / secs
+        line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": a.gpus,
+                "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1e3 * secs / max(1, a.steps),
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+                "data": "synthetic", "config": config,
+                "cpu_baseline": {"value": val, "unit": UNIT, "cores": ncores, "kind": "port",
+                                 "sample": f"{res['positions']} positions ({res['fitted']} fitted site-alleles) "
+                                           f"per step, C oracle (restatement of glm_rob_nb.r/needlestack.r; R "
+                                           f"absent), {ncores} pthreads"},
+                "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0}
+        print(json.dumps(line))
+        return 0
+
+    import torch
+    import needlestack_b200 as ns
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the B200 path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if dist is not None:
+            t = torch.zeros(1, device=dev)
+            dist.all_reduce(t)
+        torch.cuda.synchronize()
+
+    def allmax(x):
+        if dist is None:
+            return x
+        t = torch.tensor([x], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def allsum(x):
+        if dist is None:
+            return x
+        t = torch.tensor([x], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    d_ref, d_counts = generate_torch(cfg, P, cfg.seed + 1000 * rank, dev, a.p_germline)
+    torch.cuda.synchronize()
+    caller = ns.Caller(local_rank)
+    caller.set_stream(torch.cuda.current_stream().cuda_stream)
+    prm = ns.make_params()
+    fp64_peak = caller.fp64_peak_tflops()
+
+    def step_device():
+        return caller.call_snv_device(d_ref.data_ptr(), d_counts.data_ptr(), P, n, prm)
+
+    # ---- device-resident leg ----
+    for _ in range(a.warmup):
+        R = step_device()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    tm_sum = {}
+    launches = 0
+    fitted = 0
+    seeds = lattice = quad = 0
+    e0.record()
+    for _ in range(a.steps):
+        R = step_device()
+        tm = caller.timings()
+        for k, v in tm.items():
+            tm_sum[k] = tm_sum.get(k, 0) + v
+        fitted += R.n_fitted
+        seeds += R.n_seed
+        lattice += R.n_lattice
+        quad += R.n_quad
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    if a.dump_cycles and rank == 0:
+        np.savez_compressed(a.dump_cycles, cycles=R.unit_cycles, iters=R.iters, flags=R.flags, sigma=R.sigma,
+                            slope=R.slope)
+    clocks = sampler.stop()
+    ms_max = allmax(ms)
+    fitted_all = allsum(fitted)
+    launches = int(tm_sum.get("kernel_launches", 0))
+    value = fitted_all / (ms_max * 1e-3)
+    units_all = allsum(3 * P * a.steps)
+    n_emitted = R.n_emitted
+
+    # ---- rooflines (rank 0's kernels) ----
+    fit_s = tm_sum["fit_ms"] * 1e-3
+    flops = 400.0 * seeds + 32.0 * lattice + 2000.0 * quad
+    ach = flops / fit_s / 1e12 if fit_s > 0 else 0.0
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    hbm_src = "MEASURED_PEAKS.json hbm_gbs (burst)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
+    gate_s = tm_sum["gate_ms"] * 1e-3
+    gate_bytes = a.steps * (P * (36.0 * n + 1) + 3 * P * 44.0)
+    gate_ach = gate_bytes / gate_s / 1e9 if gate_s > 0 else 0.0
+    roofline = {"kernel": "k_fit", "bound": "fp64", "achieved": ach, "peak": fp64_peak, "unit": "TFLOP/s",
+                "frac": ach / fp64_peak if fp64_peak else None, "traffic": None,
+                "peak_source": "DFMA micro-benchmark run in this process (MEASURED_PEAKS.json has no FP64 entry)",
+                "flops_model": "400*N_seed + 32*N_lattice + 2000*N_quad (SURVEY.md 8d); counters from the kernel",
+                "n_seed": seeds, "n_lattice": lattice, "n_quad": quad,
+                "share_of_step": tm_sum["fit_ms"] / ms if ms else None}
+    roofline_gate = {"kernel": "k_gate", "bound": "hbm", "achieved": gate_ach, "peak": hbm_peak, "unit": "GB/s",
+                     "frac": gate_ach / hbm_peak, "traffic": None, "peak_source": hbm_src,
+                     "bytes_model": "36*n+1 B read per position + 44 B written per unit",
+                     "share_of_step": tm_sum["gate_ms"] / ms if ms else None}
+
+    # ---- end-to-end leg: host (pinned) planes in, host results out ----
+    e2e = None
+    if not a.no_e2e:
+        h_counts = ns.PinnedArray((P, 9, n), np.int32)
+        h_ref = ns.PinnedArray((P,), np.uint8)
+        torch.cuda.synchronize()
+        torch.from_numpy(h_counts.array).copy_(d_counts)
+        torch.from_numpy(h_ref.array).copy_(d_ref)
+        torch.cuda.synchronize()
+
+        def step_host():
+            return caller.call_snv(h_ref.array, h_counts.array, prm=prm)
+
+        for _ in range(min(a.warmup, 3)):
+            Rh = step_host()
+        barrier()
+        fitted_h = 0
+        e0.record()
+        for _ in range(a.steps):
+            Rh = step_host()
+            fitted_h += Rh.n_fitted
+        e1.record()
+        barrier()
+        ms_h = allmax(e0.elapsed_time(e1))
+        U = 3 * P
+        d2h = U * (8 + 8 + 8 + 4 + 4 + 4) + Rh.n_emitted * (n * 58 + 8 * 8 + 8)
+        e2e = {"value": allsum(fitted_h) / (ms_h * 1e-3), "unit": UNIT,
+               "h2d_bytes_per_step": int(h_counts.nbytes + h_ref.nbytes), "d2h_bytes_per_step": int(d2h),
+               "ms_per_step": ms_h / a.steps, "api": "needlestack_b200.Caller.call_snv -> ns_call_snv (C ABI)"}
+        assert Rh.n_fitted == R.n_fitted and Rh.n_emitted == R.n_emitted
+        ref_np = h_ref.array[: min(P, 8192)].copy()
+        counts_np = h_counts.array[: min(P, 8192)].copy()
+    else:
+        ref_np = d_ref[: min(P, 8192)].cpu().numpy()
+        counts_np = d_counts[: min(P, 8192)].cpu().numpy()
+
+    cpu = None
+    if rank == 0 and world == 1 and not a.no_cpu:
+        r = cpu_oracle_rate(ref_np, counts_np, ncores, a.cpu_seconds, {})
+        cpu = {"value": r["value"], "unit": UNIT, "cores": ncores, "kind": "port",
+               "sample": f"first {r['positions']} positions of the same batch ({r['fitted']} fitted site-alleles, "
+                         f"{r['seconds']:.1f} s), C oracle (restatement of glm_rob_nb.r/needlestack.r; R is not "
+                         f"installed on this image), {ncores} pthreads"}
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps,
+                "warmup": a.warmup, "ms_per_step": ms_max / a.steps, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config, "clocks": clocks,
+                "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "roofline_gate": roofline_gate,
+                "cpu_baseline": cpu,
+                "detail": {"site_alleles_processed_per_s": units_all / (ms_max * 1e-3),
+                           "gate_pass_fraction": fitted_all / units_all, "fitted_per_step_rank0": R.n_fitted,
+                           "emitted_per_step_rank0": n_emitted,
+                           "kernel_ms_per_step_rank0": {k: v / a.steps for k, v in tm_sum.items()
+                                                        if k.endswith("_ms")}}}
+        print(json.dumps(line))
+    caller.close()
+    if dist is not None:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -105,6 +105,7 @@ typedef struct ns_out {
     uint32_t *flags;       /* NS_F_* */
     uint32_t *iters;       /* n_outer | n_irls << 8 | n_objective_evals << 18 */
     int32_t *emit_index;   /* row in the emitted planes, or -1 */
+    uint64_t *unit_cycles; /* diagnostic: SM clock cycles the fit of each unit took (0 if gated) */
     /* emitted rows, in increasing unit order */
     int64_t emit_cap;  /* in: rows available in the planes below */
     int64_t n_emitted; /* out */

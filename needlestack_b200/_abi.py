@@ -53,7 +53,7 @@ class NsParams(C.Structure):
 
 class NsOut(C.Structure):
     _fields_ = (
-        [("sigma", c_dp), ("slope", c_dp), ("max_gq", c_dp), ("flags", c_up), ("iters", c_up), ("emit_index", c_ip),
+        [("sigma", c_dp), ("slope", c_dp), ("max_gq", c_dp), ("flags", c_up), ("iters", c_up), ("emit_index", c_ip), ("unit_cycles", C.POINTER(C.c_uint64)),
          ("emit_cap", C.c_int64), ("n_emitted", C.c_int64), ("emit_unit", c_lp)]
         + [(k, c_dp) for k in ("pvalue", "qvalue", "gq", "qval_minaf", "sor", "rvsb", "fs")]
         + [("gt", c_bp), ("status", c_bp), ("pooled", c_dp)]

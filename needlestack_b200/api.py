@@ -1,0 +1,317 @@
+"""Host-side mirror of the reference interface for the error-model path, over the C ABI of
+include/ns_b200.h (libns_b200.so, CUDA sm_100a).
+
+    glmrob_nb(y, x, ...)        <- glmrob.nb()           bin/glm_rob_nb.r:16-228
+    Caller.call_snv(ref, counts)<- per-allele SNV loop   bin/needlestack.r:321-413
+    Caller.call_units(...)      <- DEL / INS blocks      bin/needlestack.r:461-567, :624-730
+                                   annotate_vcf DP/AD    bin/annotate_vcf.r:57-69
+
+There is no CPU implementation behind these calls: a missing library or a machine without a
+CUDA device raises.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import _abi
+from ._abi import (NS_EMIT_ALL, NS_EMIT_CALLS, NS_EMIT_FITTED, NsOut, NsParams, NsTimings, c_bp, c_dp, c_ip, c_lp,
+                   c_up)
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libns_b200.so")
+_LIB = None
+
+
+class NeedlestackError(RuntimeError):
+    pass
+
+
+def load_library():
+    """dlopen libns_b200.so and declare every symbol of include/ns_b200.h (no compute calls)."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    if not os.path.exists(LIB_PATH):
+        raise NeedlestackError(f"{LIB_PATH} is missing: run `python -m needlestack_b200.build` (needs nvcc); "
+                               "there is no CPU fallback")
+    L = C.CDLL(LIB_PATH)
+    vp = C.c_void_p
+    L.ns_abi_version.restype = C.c_int
+    L.ns_params_glm_default.argtypes = [C.POINTER(NsParams)]
+    L.ns_params_caller_default.argtypes = [C.POINTER(NsParams)]
+    L.ns_create.restype = vp
+    L.ns_create.argtypes = [C.c_int, C.c_char_p, C.c_size_t]
+    L.ns_destroy.argtypes = [vp]
+    L.ns_last_error.restype = C.c_char_p
+    L.ns_last_error.argtypes = [vp]
+    L.ns_set_stream.argtypes = [vp, vp]
+    L.ns_alloc_pinned.restype = vp
+    L.ns_alloc_pinned.argtypes = [C.c_size_t]
+    L.ns_free_pinned.argtypes = [vp]
+    L.ns_get_timings.argtypes = [vp, C.POINTER(NsTimings)]
+    L.ns_call_snv.argtypes = [vp, C.POINTER(NsParams), C.c_int, C.c_int64, vp, vp, C.POINTER(NsOut)]
+    L.ns_call_snv_device.argtypes = [vp, C.POINTER(NsParams), C.c_int, C.c_int64, vp, vp, C.POINTER(NsOut)]
+    L.ns_call_units.argtypes = [vp, C.POINTER(NsParams), C.c_int, C.c_int64, vp, vp, vp, vp, vp, vp, C.c_int,
+                                C.POINTER(NsOut)]
+    L.ns_glmrob_nb.argtypes = [vp, C.POINTER(NsParams), C.c_int, vp, vp, c_dp, c_dp, c_dp, c_dp, c_dp, c_ip, c_up]
+    L.ns_measure_fp64_peak.argtypes = [vp, c_dp]
+    if L.ns_abi_version() != _abi.NS_ABI_VERSION:
+        raise NeedlestackError("libns_b200.so ABI version mismatch")
+    _LIB = L
+    return L
+
+
+EXPORTED_SYMBOLS = ("ns_abi_version", "ns_params_glm_default", "ns_params_caller_default", "ns_create", "ns_destroy",
+                    "ns_last_error", "ns_set_stream", "ns_alloc_pinned", "ns_free_pinned", "ns_get_timings",
+                    "ns_call_snv", "ns_call_snv_device", "ns_call_units", "ns_glmrob_nb", "ns_measure_fp64_peak")
+
+
+def make_params(pairs=None, defaults="caller", **kw):
+    """ns_params with needlestack.r's defaults (defaults='caller') or glmrob.nb's own ('glm')."""
+    p = NsParams()
+    vals = dict(_abi.CALLER_DEFAULTS if defaults == "caller" else dict(_abi.GLM_DEFAULTS, GQ_threshold=50.0,
+                SB_threshold_SNV=100.0, SB_threshold_indel=100.0, sigma_normal=0.1, afmin_power=-1.0,
+                emit_mode=NS_EMIT_ALL))
+    for k in kw:
+        if not hasattr(p, k):
+            raise TypeError(f"unknown parameter {k!r}")
+    vals.update(kw)
+    for k, v in vals.items():
+        setattr(p, k, v)
+    keep = []
+    if pairs is not None:
+        p.is_tn = 1
+        for name, cnt in (("tindex", "n_pairs"), ("nindex", "n_pairs"), ("only_t", "n_only_t"),
+                          ("only_n", "n_only_n")):
+            arr = np.ascontiguousarray(pairs.get(name, []), dtype=np.int32)
+            keep.append(arr)
+            setattr(p, name, arr.ctypes.data_as(c_ip))
+            setattr(p, cnt, len(arr))
+        if len(keep[0]) != len(keep[1]):
+            raise ValueError("tindex and nindex must have the same length")
+    p._keep = keep
+    return p
+
+
+class PinnedArray:
+    """numpy view over page-locked host memory from ns_alloc_pinned (the loader's target)."""
+
+    def __init__(self, shape, dtype):
+        L = load_library()
+        self.nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        self.ptr = L.ns_alloc_pinned(max(self.nbytes, 1))
+        if not self.ptr:
+            raise NeedlestackError("ns_alloc_pinned failed")
+        buf = (C.c_char * max(self.nbytes, 1)).from_address(self.ptr)
+        self.array = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+
+    def free(self):
+        if self.ptr:
+            self.array = None
+            load_library().ns_free_pinned(self.ptr)
+            self.ptr = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class Result(dict):
+    """per-unit arrays + emitted rows; attribute access for convenience"""
+    __getattr__ = dict.__getitem__
+
+    def row_of(self, unit):
+        r = int(self["emit_index"][unit])
+        return None if r < 0 else r
+
+    def dense(self, key, fill=np.nan):
+        """[U][n] array of an emitted plane with `fill` for units that were not emitted"""
+        U = len(self["flags"])
+        n = self[key].shape[1] if self[key].ndim == 2 else 0
+        out = np.full((U, n), fill, dtype=self[key].dtype)
+        idx = self["emit_index"]
+        m = idx >= 0
+        out[m] = self[key][idx[m]]
+        return out
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+class Caller:
+    """One GPU context (ns_ctx).  Not thread-safe; one per device and host thread."""
+
+    def __init__(self, device=0):
+        self._L = load_library()
+        err = C.create_string_buffer(512)
+        self._ctx = self._L.ns_create(int(device), err, 512)
+        if not self._ctx:
+            raise NeedlestackError(err.value.decode() or "ns_create failed")
+        self.device = int(device)
+
+    def close(self):
+        if getattr(self, "_ctx", None):
+            self._L.ns_destroy(self._ctx)
+            self._ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def _check(self, rc):
+        if rc != 0:
+            msg = self._L.ns_last_error(self._ctx).decode()
+            raise NeedlestackError(f"ns error {rc}: {msg}")
+
+    def set_stream(self, cuda_stream):
+        self._check(self._L.ns_set_stream(self._ctx, C.c_void_p(int(cuda_stream) if cuda_stream else 0)))
+
+    def timings(self):
+        t = NsTimings()
+        self._L.ns_get_timings(self._ctx, C.byref(t))
+        return {k: getattr(t, k) for k, _ in NsTimings._fields_}
+
+    def fp64_peak_tflops(self):
+        v = C.c_double()
+        self._check(self._L.ns_measure_fp64_peak(self._ctx, C.byref(v)))
+        return v.value
+
+    # -- output allocation ---------------------------------------------------------------
+    @staticmethod
+    def _alloc_out(U, n, emit_cap, want_rows=True):
+        o = NsOut()
+        a = dict(sigma=np.empty(U), slope=np.empty(U), max_gq=np.empty(U), flags=np.zeros(U, dtype=np.uint32),
+                 iters=np.zeros(U, dtype=np.uint32), emit_index=np.full(U, -1, dtype=np.int32),
+                 unit_cycles=np.zeros(U, dtype=np.uint64))
+        o.unit_cycles = a["unit_cycles"].ctypes.data_as(C.POINTER(C.c_uint64))
+        o.sigma, o.slope, o.max_gq = (a[k].ctypes.data_as(c_dp) for k in ("sigma", "slope", "max_gq"))
+        o.flags = a["flags"].ctypes.data_as(c_up)
+        o.iters = a["iters"].ctypes.data_as(c_up)
+        o.emit_index = a["emit_index"].ctypes.data_as(c_ip)
+        o.emit_cap = emit_cap if want_rows else 0
+        if want_rows:
+            for k in ("pvalue", "qvalue", "gq", "qval_minaf", "sor", "rvsb", "fs"):
+                a[k] = np.empty((emit_cap, n))
+                setattr(o, k, a[k].ctypes.data_as(c_dp))
+            for k in ("gt", "status"):
+                a[k] = np.zeros((emit_cap, n), dtype=np.uint8)
+                setattr(o, k, a[k].ctypes.data_as(c_bp))
+            a["pooled"] = np.empty((emit_cap, 8))
+            o.pooled = a["pooled"].ctypes.data_as(c_dp)
+            a["emit_unit"] = np.empty(emit_cap, dtype=np.int64)
+            o.emit_unit = a["emit_unit"].ctypes.data_as(c_lp)
+        return o, a
+
+    @staticmethod
+    def _finish(o, a, want_rows):
+        E = int(o.n_emitted)
+        if want_rows:
+            for k in ("pvalue", "qvalue", "gq", "qval_minaf", "sor", "rvsb", "fs", "gt", "status", "pooled",
+                      "emit_unit"):
+                a[k] = a[k][:E]
+        it = a["iters"]
+        a.update(n_emitted=E, n_fitted=int(o.n_fitted), n_gated=int(o.n_gated), n_skipped=int(o.n_skipped),
+                 n_seed=int(o.n_seed), n_lattice=int(o.n_lattice), n_quad=int(o.n_quad),
+                 n_outer=(it & 0xff).astype(np.int64), n_irls=((it >> 8) & 0x3ff).astype(np.int64),
+                 n_obj=(it >> 18).astype(np.int64))
+        return Result(a)
+
+    def _emit_cap(self, prm, U, emit_cap):
+        if emit_cap is not None:
+            return int(emit_cap)
+        if prm.emit_mode == NS_EMIT_CALLS and not prm.output_all_SNVs:
+            return max(1024, U // 16)
+        return U
+
+    def _run(self, fn, prm, U, n, emit_cap, want_rows):
+        cap = self._emit_cap(prm, U, emit_cap)
+        while True:
+            o, a = self._alloc_out(U, n, cap, want_rows)
+            rc = fn(o)
+            if rc == _abi.NS_ERR_EMIT_OVERFLOW and emit_cap is None:
+                cap = int(o.n_emitted)
+                continue
+            self._check(rc)
+            return self._finish(o, a, want_rows)
+
+    # -- the reference's per-allele SNV loop (needlestack.r:321-413) -----------------------
+    def call_snv(self, ref, counts, prm=None, emit_cap=None, want_rows=True, **kw):
+        """ref uint8 [P] (0..3 = A,T,C,G), counts int32 [P][9][n] (depth,A,T,C,G,a,t,c,g), host arrays."""
+        prm = prm or make_params(**kw)
+        counts = np.ascontiguousarray(counts, dtype=np.int32)
+        ref = np.ascontiguousarray(ref, dtype=np.uint8)
+        P, nine, n = counts.shape
+        if nine != 9 or len(ref) != P:
+            raise ValueError("counts must be [P][9][n] and ref [P]")
+        return self._run(lambda o: self._L.ns_call_snv(self._ctx, C.byref(prm), n, P, _ptr(ref), _ptr(counts),
+                                                       C.byref(o)), prm, 3 * P, n, emit_cap, want_rows)
+
+    def call_snv_device(self, d_ref_ptr, d_counts_ptr, P, n, prm, emit_cap=None, want_rows=True):
+        """same with device-resident inputs (raw device pointers, e.g. torch tensor .data_ptr())"""
+        return self._run(lambda o: self._L.ns_call_snv_device(self._ctx, C.byref(prm), n, P, C.c_void_p(d_ref_ptr),
+                                                              C.c_void_p(d_counts_ptr), C.byref(o)),
+                         prm, 3 * P, n, emit_cap, want_rows)
+
+    # -- explicit units: indel alleles, annotate_vcf, batched glmrob.nb ---------------------
+    def call_units(self, dp, vp, vm=None, rp=None, rm=None, is_indel=None, plain=False, prm=None, emit_cap=None,
+                   want_rows=True, **kw):
+        prm = prm or make_params(**kw)
+        arrs = [None if a is None else np.ascontiguousarray(a, dtype=np.int32) for a in (dp, vp, vm, rp, rm)]
+        U, n = arrs[0].shape
+        for a in arrs[1:]:
+            if a is not None and a.shape != (U, n):
+                raise ValueError("all count planes must be [U][n]")
+        ind = None if is_indel is None else np.ascontiguousarray(is_indel, dtype=np.uint8)
+        return self._run(lambda o: self._L.ns_call_units(self._ctx, C.byref(prm), n, U, *[_ptr(a) for a in arrs],
+                                                         _ptr(ind), int(bool(plain)), C.byref(o)),
+                         prm, U, n, emit_cap, want_rows)
+
+    # -- glmrob.nb(y, x, ...) (glm_rob_nb.r:16) -------------------------------------------
+    def glmrob_nb(self, y, x, bounding_func="T/T", weights_on_x="none", **kw):
+        """Mirrors glmrob.nb(): returns dict(coverage, ma_count, coef=dict(sigma, slope), pvalues, qvalues, GQ,
+        extra_rob).  Unsupported options raise with the reference's messages (glm_rob_nb.r:99,226)."""
+        if weights_on_x != "none":
+            raise NeedlestackError('Only "hard" and "none" are implemented for weights.on.x.'
+                                   if weights_on_x != "hard" else
+                                   'weights.on.x="hard" (MASS::cov.rob, random) is not available on the GPU path')
+        if bounding_func != "T/T":
+            raise NeedlestackError('Available bounding.func is "T/T"')
+        y = np.asarray(y)
+        x = np.asarray(x)
+        if y.shape != x.shape or y.ndim != 1:
+            raise ValueError("y and x must be vectors of the same length")
+        if np.any(y != np.round(y)) or np.any(x != np.round(x)) or np.any(y < 0) or np.any(x < 0):
+            raise NeedlestackError("counts must be non-negative integers")
+        yi = np.ascontiguousarray(y, dtype=np.int32)
+        xi = np.ascontiguousarray(x, dtype=np.int32)
+        n = len(yi)
+        prm = make_params(defaults="glm", **kw)
+        sigma, slope = C.c_double(), C.c_double()
+        pv, qv, gq = np.empty(n), np.empty(n), np.empty(n)
+        er, fl = C.c_int32(), C.c_uint32()
+        self._check(self._L.ns_glmrob_nb(self._ctx, C.byref(prm), n, _ptr(yi), _ptr(xi), C.byref(sigma),
+                                         C.byref(slope), pv.ctypes.data_as(c_dp), qv.ctypes.data_as(c_dp),
+                                         gq.ctypes.data_as(c_dp), C.byref(er), C.byref(fl)))
+        if fl.value & _abi.NS_F_QUAD_ERROR:
+            raise NeedlestackError("integrate() failed inside the IRLS loop (the reference stops here)")
+        return dict(coverage=np.asarray(x, dtype=float), ma_count=np.asarray(y, dtype=float),
+                    coef=dict(sigma=sigma.value, slope=slope.value), pvalues=pv, qvalues=qv, GQ=gq,
+                    extra_rob=bool(er.value), flags=fl.value)
+
+
+def glmrob_nb(y, x, device=0, **kw):
+    """Convenience one-shot glmrob.nb() on `device`."""
+    with Caller(device) as c:
+        return c.glmrob_nb(y, x, **kw)

@@ -1,0 +1,1065 @@
+/*
+ * ns_api.cu — CUDA kernels (sm_100a) and the C ABI of include/ns_b200.h.
+ *
+ * Pipeline per chunk of units (one unit = one glmrob.nb() call of the reference):
+ *   k_gate   warp per unit, streams the count rows (HBM bound): ref-inversion test,
+ *            extra-robust pre-filter, NA gate (needlestack.r:330-337, glm_rob_nb.r:20-49);
+ *            appends survivors to the fit list
+ *   k_fit    persistent warps pull units from the fit list (dynamic load balance) and run
+ *            the robust NB regression (glm_rob_nb.r:58-205) — FP64 pipe bound
+ *   k_post   p/q/GQ, Holm power q-values, T/N status, strand bias, genotypes
+ *            (glm_rob_nb.r:219-224, needlestack.r:340-409)
+ *   k_pack   gathers the rows of the emitted units, in unit order, for the D2H copy
+ * There is no CPU implementation behind this file: without a CUDA device ns_create() fails.
+ */
+#include <cuda_runtime.h>
+#include <cub/device/device_scan.cuh>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <string>
+#include <vector>
+
+#include "ns_core.cuh"
+
+#define NS_WPB_GATE 8
+#define NS_QTAB_LEN 65536
+
+/* ---- device-side bookkeeping ------------------------------------------------------- */
+struct ns_counters {
+    int n_fit, n_post, n_rows, n_emit;
+    int next_fit, next_post, pad0, pad1;
+    unsigned long long n_seed, n_lattice, n_quad, pad2;
+};
+
+struct ns_planes {
+    double *pvalue, *qvalue, *gq, *qval_minaf, *sor, *rvsb, *fs, *pooled;
+    uint8_t *gt, *status;
+};
+
+struct ns_unit_arrays {
+    uint32_t *flags, *iters;
+    unsigned long long *cycles;
+    double *sigma, *slope, *max_gq;
+    int *needrow, *row, *emitflag, *emitidx;
+    int *fit_list, *post_list;
+};
+
+extern __shared__ double ns_smem[];
+
+__global__ void __launch_bounds__(NS_WPB_GATE * 32)
+k_gate(ns_unit_src src, ns_params prm, int64_t u0, int n_units, ns_unit_arrays ua, ns_counters *cnt)
+{
+    const int n = src.n;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    double *scratch = ns_smem + (size_t)warp * (size_t)n;
+    const int wstride = gridDim.x * NS_WPB_GATE;
+    const bool emit_all = prm.emit_mode == NS_EMIT_ALL;
+    for (int u = blockIdx.x * NS_WPB_GATE + warp; u < n_units; u += wstride) {
+        ns_rows r = ns_unit_rows(src, u0 + u);
+        uint32_t flags = ns_gate_unit<WarpG>(r, n, prm, src.plain, scratch);
+        if (lane == 0) {
+            const bool gated = flags & NS_F_GATED, skipped = flags & NS_F_SKIPPED;
+            const bool out_all = (!r.is_indel) && prm.output_all_SNVs;
+            const bool need = !skipped && (!gated || emit_all || out_all);
+            ua.flags[u] = flags;
+            ua.sigma[u] = NAN;
+            ua.slope[u] = NAN;
+            ua.max_gq[u] = 0.0;
+            ua.iters[u] = 0;
+            ua.cycles[u] = 0;
+            ua.needrow[u] = need;
+            ua.emitflag[u] = 0;
+            if (!gated)
+                ua.fit_list[atomicAdd(&cnt->n_fit, 1)] = u;
+            if (need)
+                ua.post_list[atomicAdd(&cnt->n_post, 1)] = u;
+        }
+    }
+}
+
+__global__ void k_fit(ns_unit_src src, ns_params prm, int64_t u0, ns_unit_arrays ua, ns_counters *cnt)
+{
+    const int n = src.n;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    ns_work w;
+    ns_work_bind(w, ns_smem + (size_t)warp * ns_work_doubles(n), n);
+    unsigned long long tot_seed = 0, tot_lat = 0, tot_quad = 0;
+    const int n_fit = cnt->n_fit;
+    for (;;) {
+        int idx = 0;
+        if (lane == 0)
+            idx = atomicAdd(&cnt->next_fit, 1);
+        idx = __shfl_sync(0xffffffffu, idx, 0);
+        if (idx >= n_fit)
+            break;
+        const int u = ua.fit_list[idx];
+        const long long t_start = clock64();
+        const uint32_t flags = ua.flags[u];
+        ns_rows r = ns_unit_rows(src, u0 + u);
+        const bool inv = flags & NS_F_REF_INV, extra = flags & NS_F_EXTRA_ROB;
+        double maxmu = -INFINITY;
+        for (int i = lane; i < n; i += 32) {
+            double x = ns_ld(r.dp, i);
+            double y = inv ? ns_ld(r.rp, i) + ns_ld(r.rm, i) : ns_ld(r.vp, i) + ns_ld(r.vm, i);
+            maxmu = fmax(maxmu, x);
+            bool keep = !(extra && y / x > prm.min_af_extra_rob);
+            w.y[i] = y;
+            w.x[i] = keep ? x : 0.0;
+        }
+        maxmu = WarpG::max(maxmu);
+        __syncwarp();
+        ns_fit_result res;
+        ns_fit_unit<WarpG>(w, n, maxmu, prm, res);
+        tot_seed += res.cnt.n_seed;
+        tot_lat += res.cnt.n_lattice;
+        tot_quad += res.cnt.n_quad;
+        if (lane == 0) {
+            ua.sigma[u] = res.sigma;
+            ua.slope[u] = res.slope;
+            ua.flags[u] = flags | res.flags;
+            unsigned no = res.n_outer > 255 ? 255 : res.n_outer, ni = res.n_irls > 1023 ? 1023 : res.n_irls,
+                     nj = res.n_obj > 16383 ? 16383 : res.n_obj;
+            ua.iters[u] = no | (ni << 8) | (nj << 18);
+            ua.cycles[u] = (unsigned long long)(clock64() - t_start);
+        }
+        __syncwarp();
+    }
+    /* per-lane counters -> warp -> global */
+    for (int o = 16; o > 0; o >>= 1) {
+        tot_seed += __shfl_xor_sync(0xffffffffu, tot_seed, o);
+        tot_lat += __shfl_xor_sync(0xffffffffu, tot_lat, o);
+        tot_quad += __shfl_xor_sync(0xffffffffu, tot_quad, o);
+    }
+    if (lane == 0 && (tot_seed | tot_lat | tot_quad)) {
+        atomicAdd(&cnt->n_seed, tot_seed);
+        atomicAdd(&cnt->n_lattice, tot_lat);
+        atomicAdd(&cnt->n_quad, tot_quad);
+    }
+}
+
+__global__ void k_post(ns_unit_src src, ns_params prm, int64_t u0, ns_unit_arrays ua, ns_planes pl,
+                       const double *qtab, int qtab_len, ns_counters *cnt)
+{
+    const int n = src.n;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    double *sm = ns_smem + (size_t)warp * (3 * (size_t)n + 8);
+    const int n_post = cnt->n_post;
+    for (;;) {
+        int idx = 0;
+        if (lane == 0)
+            idx = atomicAdd(&cnt->next_post, 1);
+        idx = __shfl_sync(0xffffffffu, idx, 0);
+        if (idx >= n_post)
+            break;
+        const int u = ua.post_list[idx];
+        const size_t row = (size_t)ua.row[u];
+        ns_rows r = ns_unit_rows(src, u0 + u);
+        ns_unit_out o;
+        o.pvalue = pl.pvalue + row * n;
+        o.qvalue = pl.qvalue + row * n;
+        o.gq = pl.gq + row * n;
+        o.qval_minaf = pl.qval_minaf + row * n;
+        o.sor = pl.sor + row * n;
+        o.rvsb = pl.rvsb + row * n;
+        o.fs = pl.fs + row * n;
+        o.gt = pl.gt + row * n;
+        o.status = pl.status + row * n;
+        o.pooled = pl.pooled + row * 8;
+        if (lane < 8)
+            o.pooled[lane] = NAN;
+        double mg = 0;
+        uint32_t flags = ns_post_unit<WarpG>(r, n, prm, ua.flags[u], ua.sigma[u], ua.slope[u], qtab, qtab_len,
+                                             o, sm, mg);
+        if (lane == 0) {
+            ua.flags[u] = flags;
+            ua.max_gq[u] = mg;
+            bool emit = prm.emit_mode == NS_EMIT_ALL || (prm.emit_mode == NS_EMIT_FITTED && !(flags & NS_F_GATED)) ||
+                        (flags & NS_F_GATE2);
+            ua.emitflag[u] = emit;
+        }
+        __syncwarp();
+    }
+}
+
+__global__ void k_scan_total(const int *flag, const int *excl, int n, int *total)
+{
+    if (threadIdx.x == 0 && blockIdx.x == 0)
+        *total = n > 0 ? excl[n - 1] + flag[n - 1] : 0;
+}
+
+/* rows of emitted units, in unit order, into the packed planes */
+__global__ void k_pack(int n, int n_units, int64_t u0, int64_t emit_off, int cap, ns_unit_arrays ua,
+                       ns_planes src, ns_planes dst, int64_t *emit_unit, int *emit_index_out)
+{
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int wpb = blockDim.x >> 5;
+    for (int u = blockIdx.x * wpb + warp; u < n_units; u += gridDim.x * wpb) {
+        if (!ua.emitflag[u]) {
+            if (lane == 0)
+                emit_index_out[u] = -1;
+            continue;
+        }
+        const int d = ua.emitidx[u];
+        if (lane == 0)
+            emit_index_out[u] = (int)(emit_off + d);
+        if (d >= cap)
+            continue;
+        const size_t so = (size_t)ua.row[u] * n, dof = (size_t)d * n;
+        for (int i = lane; i < n; i += 32) {
+            dst.pvalue[dof + i] = src.pvalue[so + i];
+            dst.qvalue[dof + i] = src.qvalue[so + i];
+            dst.gq[dof + i] = src.gq[so + i];
+            dst.qval_minaf[dof + i] = src.qval_minaf[so + i];
+            dst.sor[dof + i] = src.sor[so + i];
+            dst.rvsb[dof + i] = src.rvsb[so + i];
+            dst.fs[dof + i] = src.fs[so + i];
+            dst.gt[dof + i] = src.gt[so + i];
+            dst.status[dof + i] = src.status[so + i];
+        }
+        if (lane < 8)
+            dst.pooled[(size_t)d * 8 + lane] = src.pooled[(size_t)ua.row[u] * 8 + lane];
+        if (lane == 0)
+            emit_unit[d] = u0 + u;
+    }
+}
+
+/* y* tables of toQvalueN / toQvalueT (needlestack.r:243,249): they depend on the depth only */
+__global__ void k_qtab(double *tabN, double *tabT, int len, double sigma_normal, double afmin)
+{
+    int x = blockIdx.x * blockDim.x + threadIdx.x;
+    if (x >= len)
+        return;
+    tabN[x] = ns_qnbinom_mu(0.01, 1 / sigma_normal, 0.5 * (double)x);
+    if (tabT)
+        tabT[x] = (afmin >= 0) ? ns_qbinom(0.01, (double)x, afmin) : 0.0;
+}
+
+/* DFMA throughput probe: 8 independent chains per thread */
+__global__ void k_dfma(double *out, int iters, double a, double b)
+{
+    double x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6,
+           x7 = x0 + 7;
+    for (int i = 0; i < iters; i++) {
+        x0 = fma(x0, a, b);
+        x1 = fma(x1, a, b);
+        x2 = fma(x2, a, b);
+        x3 = fma(x3, a, b);
+        x4 = fma(x4, a, b);
+        x5 = fma(x5, a, b);
+        x6 = fma(x6, a, b);
+        x7 = fma(x7, a, b);
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7;
+}
+
+/* ---- host side ----------------------------------------------------------------------- */
+template <class T> struct DevBuf {
+    T *p = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t n)
+    {
+        if (n <= cap)
+            return cudaSuccess;
+        if (p)
+            cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = n + n / 8 + 64;
+        cudaError_t e = cudaMalloc((void **)&p, want * sizeof(T));
+        if (e == cudaSuccess)
+            cap = want;
+        return e;
+    }
+    void release()
+    {
+        if (p)
+            cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+struct PlaneSet {
+    DevBuf<double> pvalue, qvalue, gq, qval_minaf, sor, rvsb, fs, pooled;
+    DevBuf<uint8_t> gt, status;
+    cudaError_t reserve(size_t rows, int n)
+    {
+        cudaError_t e;
+        size_t m = rows * (size_t)n;
+        if ((e = pvalue.reserve(m)) || (e = qvalue.reserve(m)) || (e = gq.reserve(m)) || (e = qval_minaf.reserve(m)) ||
+            (e = sor.reserve(m)) || (e = rvsb.reserve(m)) || (e = fs.reserve(m)) || (e = pooled.reserve(rows * 8)) ||
+            (e = gt.reserve(m)) || (e = status.reserve(m)))
+            return e;
+        return cudaSuccess;
+    }
+    ns_planes view()
+    {
+        ns_planes v = {pvalue.p, qvalue.p, gq.p, qval_minaf.p, sor.p, rvsb.p, fs.p, pooled.p, gt.p, status.p};
+        return v;
+    }
+    void release()
+    {
+        pvalue.release(), qvalue.release(), gq.release(), qval_minaf.release(), sor.release(), rvsb.release(),
+            fs.release(), pooled.release(), gt.release(), status.release();
+    }
+};
+
+struct ns_ctx {
+    int device = 0;
+    int sm_count = 148;
+    cudaStream_t stream = nullptr, own_stream = nullptr, copy_stream = nullptr;
+    std::string err;
+    /* staging of host inputs, double buffered */
+    DevBuf<int32_t> in_counts[2];
+    DevBuf<uint8_t> in_ref[2];
+    DevBuf<int32_t> in_rows[5];
+    DevBuf<uint8_t> in_indel;
+    cudaEvent_t ev_h2d[2], ev_free[2];
+    /* per-chunk unit arrays */
+    DevBuf<uint32_t> flags, iters;
+    DevBuf<unsigned long long> cycles;
+    DevBuf<double> sigma, slope, max_gq;
+    DevBuf<int> needrow, row, emitflag, emitidx, fit_list, post_list, emit_index_out;
+    DevBuf<int64_t> emit_unit;
+    DevBuf<ns_counters> counters;
+    DevBuf<unsigned char> cub_tmp;
+    PlaneSet rows, packed;
+    size_t packed_cap = 0;
+    /* parameter-dependent device state */
+    DevBuf<int32_t> pair_idx;
+    DevBuf<uint8_t> role;
+    DevBuf<double> qtabN, qtabT;
+    double qtab_sigma = -1, qtab_afmin = -2;
+    /* timings */
+    cudaEvent_t ev[10];
+    ns_timings tm;
+    ns_counters *h_counters = nullptr; /* pinned */
+    int64_t chunk_units = 0;           /* 0 = auto */
+};
+
+#define CK(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess) {                                                                   \
+            char b_[512];                                                                          \
+            snprintf(b_, sizeof b_, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+            ctx->err = b_;                                                                         \
+            return NS_ERR_CUDA;                                                                    \
+        }                                                                                          \
+    } while (0)
+
+extern "C" {
+
+int ns_abi_version(void) { return NS_ABI_VERSION; }
+
+void ns_params_glm_default(ns_params *p)
+{ /* bin/glm_rob_nb.r:16-18 */
+    memset(p, 0, sizeof(*p));
+    p->c_tukey_beta = 5;
+    p->c_tukey_sig = 3;
+    p->minsig = 1e-3;
+    p->maxsig = 10;
+    p->minmu = 1e-10;
+    p->sig_prec = 1e-8;
+    p->tol = 1e-6;
+    p->maxit = 30;
+    p->maxit_sig = 50;
+    p->n_ai_sig_tukey = 100;
+    p->min_coverage = 1;
+    p->min_reads = 1;
+    p->min_af = 0;
+    p->size_min = 10;
+    p->extra_rob = 1;
+    p->min_af_extra_rob = 0.2;
+    p->min_prop_extra_rob = 0.1;
+    p->max_prop_extra_rob = 0.5;
+    p->GQ_threshold = 50;
+    p->SB_threshold_SNV = 100;
+    p->SB_threshold_indel = 100;
+    p->sigma_normal = 0.1;
+    p->afmin_power = -1;
+    p->emit_mode = NS_EMIT_ALL;
+}
+
+void ns_params_caller_default(ns_params *p)
+{ /* bin/needlestack.r:64-92 */
+    ns_params_glm_default(p);
+    p->min_coverage = 30;
+    p->min_reads = 3;
+    p->min_af = 0;
+    p->extra_rob = 0;
+    p->max_prop_extra_rob = 0.8;
+    p->SB_type = 0;
+    p->emit_mode = NS_EMIT_CALLS;
+}
+
+ns_ctx *ns_create(int device, char *err, size_t errlen)
+{
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0 || device < 0 || device >= ndev) {
+        if (err && errlen)
+            snprintf(err, errlen, "ns_create: no usable CUDA device %d (%s, %d devices); this library has no CPU path",
+                     device, cudaGetErrorString(e), ndev);
+        return nullptr;
+    }
+    cudaSetDevice(device);
+    cudaDeviceProp prop;
+    cudaGetDeviceProperties(&prop, device);
+    if (prop.major < 10) {
+        if (err && errlen)
+            snprintf(err, errlen, "ns_create: device %d is sm_%d%d; this library is built for sm_100a (B200) only",
+                     device, prop.major, prop.minor);
+        return nullptr;
+    }
+    ns_ctx *ctx = new ns_ctx();
+    ctx->device = device;
+    ctx->sm_count = prop.multiProcessorCount;
+    bool ok = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) == cudaSuccess &&
+              cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) == cudaSuccess;
+    for (int i = 0; i < 2 && ok; i++)
+        ok = cudaEventCreateWithFlags(&ctx->ev_h2d[i], cudaEventDisableTiming) == cudaSuccess &&
+             cudaEventCreateWithFlags(&ctx->ev_free[i], cudaEventDisableTiming) == cudaSuccess;
+    for (int i = 0; i < 10 && ok; i++)
+        ok = cudaEventCreate(&ctx->ev[i]) == cudaSuccess;
+    ok = ok && cudaMallocHost((void **)&ctx->h_counters, sizeof(ns_counters)) == cudaSuccess;
+    ok = ok && ctx->counters.reserve(1) == cudaSuccess;
+    if (!ok) {
+        if (err && errlen)
+            snprintf(err, errlen, "ns_create: CUDA resource creation failed: %s", cudaGetErrorString(cudaGetLastError()));
+        delete ctx;
+        return nullptr;
+    }
+    ctx->stream = ctx->own_stream;
+    memset(&ctx->tm, 0, sizeof(ctx->tm));
+    const char *cu = getenv("NS_CHUNK_UNITS");
+    if (cu)
+        ctx->chunk_units = atoll(cu);
+    return ctx;
+}
+
+void ns_destroy(ns_ctx *ctx)
+{
+    if (!ctx)
+        return;
+    cudaSetDevice(ctx->device);
+    cudaDeviceSynchronize();
+    for (int i = 0; i < 2; i++) {
+        ctx->in_counts[i].release();
+        ctx->in_ref[i].release();
+        cudaEventDestroy(ctx->ev_h2d[i]);
+        cudaEventDestroy(ctx->ev_free[i]);
+    }
+    for (int i = 0; i < 5; i++)
+        ctx->in_rows[i].release();
+    ctx->in_indel.release();
+    ctx->flags.release(), ctx->iters.release(), ctx->cycles.release(), ctx->sigma.release(), ctx->slope.release(), ctx->max_gq.release();
+    ctx->needrow.release(), ctx->row.release(), ctx->emitflag.release(), ctx->emitidx.release();
+    ctx->fit_list.release(), ctx->post_list.release(), ctx->emit_index_out.release(), ctx->emit_unit.release();
+    ctx->counters.release(), ctx->cub_tmp.release(), ctx->rows.release(), ctx->packed.release();
+    ctx->pair_idx.release(), ctx->role.release(), ctx->qtabN.release(), ctx->qtabT.release();
+    for (int i = 0; i < 10; i++)
+        cudaEventDestroy(ctx->ev[i]);
+    if (ctx->h_counters)
+        cudaFreeHost(ctx->h_counters);
+    cudaStreamDestroy(ctx->own_stream);
+    cudaStreamDestroy(ctx->copy_stream);
+    delete ctx;
+}
+
+const char *ns_last_error(ns_ctx *ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+int ns_set_stream(ns_ctx *ctx, void *cuda_stream)
+{
+    if (!ctx)
+        return NS_ERR_ARG;
+    ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
+    return NS_OK;
+}
+
+void *ns_alloc_pinned(size_t bytes)
+{
+    void *p = nullptr;
+    if (cudaMallocHost(&p, bytes) != cudaSuccess)
+        return nullptr;
+    return p;
+}
+void ns_free_pinned(void *p)
+{
+    if (p)
+        cudaFreeHost(p);
+}
+
+int ns_get_timings(ns_ctx *ctx, ns_timings *t)
+{
+    if (!ctx || !t)
+        return NS_ERR_ARG;
+    *t = ctx->tm;
+    return NS_OK;
+}
+
+int ns_measure_fp64_peak(ns_ctx *ctx, double *tflops)
+{
+    if (!ctx || !tflops)
+        return NS_ERR_ARG;
+    cudaSetDevice(ctx->device);
+    const int blocks = ctx->sm_count * 8, threads = 256, iters = 1 << 14;
+    DevBuf<double> out;
+    CK(out.reserve((size_t)blocks * threads));
+    double best = 0;
+    for (int rep = 0; rep < 4; rep++) {
+        CK(cudaEventRecord(ctx->ev[0], ctx->stream));
+        k_dfma<<<blocks, threads, 0, ctx->stream>>>(out.p, iters, 0.999999, 1e-9);
+        CK(cudaEventRecord(ctx->ev[1], ctx->stream));
+        CK(cudaEventSynchronize(ctx->ev[1]));
+        float ms = 0;
+        CK(cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]));
+        double fl = 2.0 * 8.0 * (double)iters * (double)blocks * (double)threads;
+        double tf = fl / (ms * 1e-3) / 1e12;
+        if (rep > 0 && tf > best)
+            best = tf;
+    }
+    out.release();
+    *tflops = best;
+    return NS_OK;
+}
+
+} /* extern "C" */
+
+/* upload pair index sets, build the role array and the y* tables; returns device params */
+static int ns_prepare_params(ns_ctx *ctx, const ns_params *in, int n, ns_params *dprm, const double **qtab)
+{
+    *dprm = *in;
+    if (in->n_ai_sig_tukey < 3 || in->n_ai_sig_tukey > NS_MAX_KNOTS) {
+        ctx->err = "n_ai.sig.tukey must be in [3, 128]";
+        return NS_ERR_ARG;
+    }
+    dprm->tindex = dprm->nindex = dprm->only_t = dprm->only_n = nullptr;
+    dprm->role = nullptr;
+    if (in->is_tn) {
+        const int np = in->n_pairs, nt = in->n_only_t, nn = in->n_only_n;
+        if (np < 0 || nt < 0 || nn < 0 || (np > 0 && (!in->tindex || !in->nindex)) || (nt > 0 && !in->only_t) ||
+            (nn > 0 && !in->only_n)) {
+            ctx->err = "tumour/normal index sets missing";
+            return NS_ERR_ARG;
+        }
+        std::vector<int32_t> h((size_t)2 * np + nt + nn + 4);
+        std::vector<uint8_t> role((size_t)n, 0);
+        auto chk = [&](const int32_t *a, int m) {
+            for (int i = 0; i < m; i++)
+                if (a[i] < 0 || a[i] >= n)
+                    return false;
+            return true;
+        };
+        if (!chk(in->tindex, np) || !chk(in->nindex, np) || !chk(in->only_t, nt) || !chk(in->only_n, nn)) {
+            ctx->err = "tumour/normal sample index out of range";
+            return NS_ERR_ARG;
+        }
+        /* assignment order of needlestack.r:343-347: N of pairs, T of pairs, only N, only T */
+        for (int i = 0; i < np; i++)
+            h[i] = in->tindex[i], h[np + i] = in->nindex[i];
+        for (int i = 0; i < nt; i++)
+            h[2 * np + i] = in->only_t[i];
+        for (int i = 0; i < nn; i++)
+            h[2 * np + nt + i] = in->only_n[i];
+        for (int i = 0; i < np; i++)
+            role[in->nindex[i]] = 1;
+        for (int i = 0; i < np; i++)
+            role[in->tindex[i]] = 2;
+        for (int i = 0; i < nn; i++)
+            role[in->only_n[i]] = 3;
+        for (int i = 0; i < nt; i++)
+            role[in->only_t[i]] = 4;
+        CK(ctx->pair_idx.reserve(h.size()));
+        CK(ctx->role.reserve((size_t)n));
+        CK(cudaMemcpyAsync(ctx->pair_idx.p, h.data(), h.size() * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemcpyAsync(ctx->role.p, role.data(), (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        dprm->tindex = ctx->pair_idx.p;
+        dprm->nindex = ctx->pair_idx.p + np;
+        dprm->only_t = ctx->pair_idx.p + 2 * np;
+        dprm->only_n = ctx->pair_idx.p + 2 * np + nt;
+        dprm->role = ctx->role.p;
+    }
+    double afmin = in->afmin_power;
+    if (in->is_tn && afmin == -1)
+        afmin = 0.01;
+    if (ctx->qtab_sigma != in->sigma_normal || ctx->qtab_afmin != afmin || !ctx->qtabN.p) {
+        CK(ctx->qtabN.reserve(NS_QTAB_LEN));
+        k_qtab<<<(NS_QTAB_LEN + 127) / 128, 128, 0, ctx->stream>>>(ctx->qtabN.p, nullptr, NS_QTAB_LEN, in->sigma_normal,
+                                                                  afmin);
+        CK(cudaGetLastError());
+        ctx->qtab_sigma = in->sigma_normal;
+        ctx->qtab_afmin = afmin;
+        ctx->tm.kernel_launches++;
+    }
+    *qtab = ctx->qtabN.p;
+    return NS_OK;
+}
+
+static cudaError_t ns_reserve_units(ns_ctx *ctx, size_t U)
+{
+    cudaError_t e;
+    if ((e = ctx->flags.reserve(U)) || (e = ctx->iters.reserve(U)) || (e = ctx->cycles.reserve(U)) || (e = ctx->sigma.reserve(U)) ||
+        (e = ctx->slope.reserve(U)) || (e = ctx->max_gq.reserve(U)) || (e = ctx->needrow.reserve(U)) ||
+        (e = ctx->row.reserve(U)) || (e = ctx->emitflag.reserve(U)) || (e = ctx->emitidx.reserve(U)) ||
+        (e = ctx->fit_list.reserve(U)) || (e = ctx->post_list.reserve(U)) || (e = ctx->emit_index_out.reserve(U)))
+        return e;
+    size_t tmp = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, tmp, (int *)nullptr, (int *)nullptr, (int)U);
+    return ctx->cub_tmp.reserve(tmp + 256);
+}
+
+static float ev_ms(cudaEvent_t a, cudaEvent_t b)
+{
+    float ms = 0;
+    cudaEventElapsedTime(&ms, a, b);
+    return ms;
+}
+
+/* one chunk of units whose inputs are on the device; results to host at unit offset u_off */
+static int ns_run_chunk(ns_ctx *ctx, const ns_params &dprm, const double *qtab, const ns_unit_src &src, int64_t u0_src,
+                        int64_t u_off, int U, ns_out *out, int64_t *emit_off)
+{
+    const int n = src.n;
+    cudaStream_t st = ctx->stream;
+    cudaError_t ce = ns_reserve_units(ctx, (size_t)U);
+    if (ce != cudaSuccess) {
+        ctx->err = std::string("device allocation (unit arrays) failed: ") + cudaGetErrorString(ce);
+        return NS_ERR_NOMEM;
+    }
+    ns_unit_arrays ua = {ctx->flags.p,    ctx->iters.p,    ctx->cycles.p,   ctx->sigma.p,   ctx->slope.p,    ctx->max_gq.p,  ctx->needrow.p,
+                         ctx->row.p,      ctx->emitflag.p, ctx->emitidx.p, ctx->fit_list.p, ctx->post_list.p};
+    CK(cudaMemsetAsync(ctx->counters.p, 0, sizeof(ns_counters), st));
+    /* gate */
+    CK(cudaEventRecord(ctx->ev[0], st));
+    {
+        int blocks = (U + NS_WPB_GATE - 1) / NS_WPB_GATE;
+        int maxb = ctx->sm_count * 8;
+        if (blocks > maxb)
+            blocks = maxb;
+        size_t sm = (size_t)NS_WPB_GATE * n * sizeof(double);
+        if (sm > 48 * 1024)
+            CK(cudaFuncSetAttribute(k_gate, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+        k_gate<<<blocks, NS_WPB_GATE * 32, sm, st>>>(src, dprm, u0_src, U, ua, ctx->counters.p);
+        CK(cudaGetLastError());
+    }
+    CK(cudaEventRecord(ctx->ev[1], st));
+    /* rows for the units that need per-sample planes */
+    {
+        size_t tmp = ctx->cub_tmp.cap;
+        CK(cub::DeviceScan::ExclusiveSum(ctx->cub_tmp.p, tmp, ctx->needrow.p, ctx->row.p, U, st));
+        k_scan_total<<<1, 32, 0, st>>>(ctx->needrow.p, ctx->row.p, U, &ctx->counters.p->n_rows);
+    }
+    CK(cudaMemcpyAsync(ctx->h_counters, ctx->counters.p, sizeof(ns_counters), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    const int n_rows = ctx->h_counters->n_rows, n_fit = ctx->h_counters->n_fit;
+    ce = ctx->rows.reserve((size_t)(n_rows > 0 ? n_rows : 1), n);
+    if (ce != cudaSuccess) {
+        ctx->err = std::string("device allocation (result planes) failed: ") + cudaGetErrorString(ce);
+        return NS_ERR_NOMEM;
+    }
+    /* fit */
+    CK(cudaEventRecord(ctx->ev[2], st));
+    if (n_fit > 0) {
+        int wpb = 4;
+        size_t per_warp = ns_work_doubles(n) * sizeof(double);
+        while (wpb > 1 && wpb * per_warp > 200 * 1024)
+            wpb >>= 1;
+        size_t sm = wpb * per_warp;
+        if (sm > 227 * 1024) {
+            ctx->err = "too many samples for the on-chip working set (n > ~4700)";
+            return NS_ERR_ARG;
+        }
+        if (sm > 48 * 1024)
+            CK(cudaFuncSetAttribute(k_fit, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+        int bps = 0;
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_fit, wpb * 32, sm));
+        if (bps < 1)
+            bps = 1;
+        int blocks = ctx->sm_count * bps;
+        int need = (n_fit + wpb - 1) / wpb;
+        if (blocks > need)
+            blocks = need;
+        k_fit<<<blocks, wpb * 32, sm, st>>>(src, dprm, u0_src, ua, ctx->counters.p);
+        CK(cudaGetLastError());
+        ctx->tm.kernel_launches++;
+    }
+    CK(cudaEventRecord(ctx->ev[3], st));
+    /* post */
+    const int n_post = ctx->h_counters->n_post;
+    if (n_post > 0) {
+        int wpb = 4;
+        size_t per_warp = (3 * (size_t)n + 8) * sizeof(double);
+        while (wpb > 1 && wpb * per_warp > 200 * 1024)
+            wpb >>= 1;
+        size_t sm = wpb * per_warp;
+        if (sm > 48 * 1024)
+            CK(cudaFuncSetAttribute(k_post, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+        int bps = 0;
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_post, wpb * 32, sm));
+        if (bps < 1)
+            bps = 1;
+        int blocks = ctx->sm_count * bps;
+        int need = (n_post + wpb - 1) / wpb;
+        if (blocks > need)
+            blocks = need;
+        k_post<<<blocks, wpb * 32, sm, st>>>(src, dprm, u0_src, ua, ctx->rows.view(), qtab, NS_QTAB_LEN,
+                                            ctx->counters.p);
+        CK(cudaGetLastError());
+        ctx->tm.kernel_launches++;
+    }
+    CK(cudaEventRecord(ctx->ev[4], st));
+    /* emitted rows */
+    {
+        size_t tmp = ctx->cub_tmp.cap;
+        CK(cub::DeviceScan::ExclusiveSum(ctx->cub_tmp.p, tmp, ctx->emitflag.p, ctx->emitidx.p, U, st));
+        k_scan_total<<<1, 32, 0, st>>>(ctx->emitflag.p, ctx->emitidx.p, U, &ctx->counters.p->n_emit);
+    }
+    CK(cudaMemcpyAsync(ctx->h_counters, ctx->counters.p, sizeof(ns_counters), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    const int n_emit = ctx->h_counters->n_emit;
+    const bool want_rows = out->pvalue || out->qvalue || out->gq || out->qval_minaf || out->sor || out->rvsb ||
+                           out->fs || out->gt || out->status || out->pooled || out->emit_unit;
+    int64_t room = out->emit_cap - *emit_off;
+    if (room < 0)
+        room = 0;
+    const int n_copy = (int)((int64_t)n_emit < room ? n_emit : room);
+    {
+        /* buffers only ever grow; the row capacity depends on the current n */
+        size_t cap = (size_t)n_emit + 1024;
+        ce = ctx->packed.reserve(cap, n);
+        if (ce == cudaSuccess)
+            ce = ctx->emit_unit.reserve(cap);
+        if (ce != cudaSuccess) {
+            ctx->err = std::string("device allocation (packed planes) failed: ") + cudaGetErrorString(ce);
+            return NS_ERR_NOMEM;
+        }
+        ctx->packed_cap = cap;
+    }
+    {
+        int wpb = 8;
+        int blocks = (U + wpb - 1) / wpb;
+        if (blocks > ctx->sm_count * 8)
+            blocks = ctx->sm_count * 8;
+        k_pack<<<blocks, wpb * 32, 0, st>>>(n, U, u_off, *emit_off, (int)ctx->packed_cap, ua, ctx->rows.view(),
+                                            ctx->packed.view(), ctx->emit_unit.p, ctx->emit_index_out.p);
+        CK(cudaGetLastError());
+    }
+    CK(cudaEventRecord(ctx->ev[5], st));
+    /* D2H */
+#define D2H(dst, srcp, count, type)                                                                \
+    if (dst)                                                                                       \
+    CK(cudaMemcpyAsync((dst), (srcp), (size_t)(count) * sizeof(type), cudaMemcpyDeviceToHost, st))
+    D2H(out->sigma ? out->sigma + u_off : nullptr, ctx->sigma.p, U, double);
+    D2H(out->slope ? out->slope + u_off : nullptr, ctx->slope.p, U, double);
+    D2H(out->max_gq ? out->max_gq + u_off : nullptr, ctx->max_gq.p, U, double);
+    D2H(out->flags ? out->flags + u_off : nullptr, ctx->flags.p, U, uint32_t);
+    D2H(out->iters ? out->iters + u_off : nullptr, ctx->iters.p, U, uint32_t);
+    D2H(out->unit_cycles ? out->unit_cycles + u_off : nullptr, ctx->cycles.p, U, uint64_t);
+    D2H(out->emit_index ? out->emit_index + u_off : nullptr, ctx->emit_index_out.p, U, int32_t);
+    if (want_rows && n_copy > 0) {
+        const size_t eo = (size_t)*emit_off;
+        const size_t m = (size_t)n_copy * n;
+        ns_planes pk = ctx->packed.view();
+        D2H(out->pvalue ? out->pvalue + eo * n : nullptr, pk.pvalue, m, double);
+        D2H(out->qvalue ? out->qvalue + eo * n : nullptr, pk.qvalue, m, double);
+        D2H(out->gq ? out->gq + eo * n : nullptr, pk.gq, m, double);
+        D2H(out->qval_minaf ? out->qval_minaf + eo * n : nullptr, pk.qval_minaf, m, double);
+        D2H(out->sor ? out->sor + eo * n : nullptr, pk.sor, m, double);
+        D2H(out->rvsb ? out->rvsb + eo * n : nullptr, pk.rvsb, m, double);
+        D2H(out->fs ? out->fs + eo * n : nullptr, pk.fs, m, double);
+        D2H(out->gt ? out->gt + eo * n : nullptr, pk.gt, m, uint8_t);
+        D2H(out->status ? out->status + eo * n : nullptr, pk.status, m, uint8_t);
+        D2H(out->pooled ? out->pooled + eo * 8 : nullptr, pk.pooled, (size_t)n_copy * 8, double);
+        D2H(out->emit_unit ? out->emit_unit + eo : nullptr, ctx->emit_unit.p, n_copy, int64_t);
+    }
+#undef D2H
+    CK(cudaEventRecord(ctx->ev[6], st));
+    CK(cudaStreamSynchronize(st));
+    ctx->tm.gate_ms += ev_ms(ctx->ev[0], ctx->ev[1]);
+    ctx->tm.fit_ms += ev_ms(ctx->ev[2], ctx->ev[3]);
+    ctx->tm.post_ms += ev_ms(ctx->ev[3], ctx->ev[4]);
+    ctx->tm.pack_ms += ev_ms(ctx->ev[4], ctx->ev[5]);
+    ctx->tm.d2h_ms += ev_ms(ctx->ev[5], ctx->ev[6]);
+    ctx->tm.kernel_launches += 8; /* gate, 2 x (cub scan = init + scan kernels, total), pack */
+    *emit_off += n_emit;
+    out->n_fitted += n_fit;
+    out->n_seed += ctx->h_counters->n_seed;
+    out->n_lattice += ctx->h_counters->n_lattice;
+    out->n_quad += ctx->h_counters->n_quad;
+    return NS_OK;
+}
+
+static int64_t ns_pick_chunk(ns_ctx *ctx, int n, int64_t total_units)
+{
+    if (ctx->chunk_units > 0)
+        return ctx->chunk_units;
+    /* bound the per-chunk result planes (58 B per sample per row) to ~1.5 GB */
+    int64_t c = (int64_t)(1500.0e6 / (58.0 * n));
+    if (c > 3 * 131072)
+        c = 3 * 131072;
+    if (c < 3 * 256)
+        c = 3 * 256;
+    c -= c % 3;
+    if (c > total_units)
+        c = total_units;
+    return c;
+}
+
+static void ns_reset_out(ns_ctx *ctx, ns_out *out)
+{
+    out->n_emitted = 0;
+    out->n_fitted = out->n_gated = out->n_skipped = 0;
+    out->n_seed = out->n_lattice = out->n_quad = 0;
+    memset(&ctx->tm, 0, sizeof(ctx->tm));
+}
+
+static void ns_finish_out(ns_out *out, int64_t total_units, int64_t emitted)
+{
+    out->n_emitted = emitted;
+    out->n_gated = total_units - out->n_fitted;
+    if (out->flags) {
+        int64_t sk = 0;
+        for (int64_t u = 0; u < total_units; u++)
+            sk += (out->flags[u] & NS_F_SKIPPED) != 0;
+        out->n_skipped = sk;
+        out->n_gated -= sk;
+    }
+}
+
+extern "C" {
+
+int ns_call_snv_device(ns_ctx *ctx, const ns_params *prm, int n, int64_t P, const uint8_t *d_ref,
+                       const int32_t *d_counts, ns_out *out)
+{
+    if (!ctx)
+        return NS_ERR_ARG;
+    if (!prm || !out || n < 1 || P < 0 || (P > 0 && (!d_ref || !d_counts))) {
+        ctx->err = "ns_call_snv_device: bad argument";
+        return NS_ERR_ARG;
+    }
+    CK(cudaSetDevice(ctx->device));
+    ns_reset_out(ctx, out);
+    ns_params dprm;
+    const double *qtab = nullptr;
+    int rc = ns_prepare_params(ctx, prm, n, &dprm, &qtab);
+    if (rc)
+        return rc;
+    cudaEvent_t t0 = ctx->ev[8], t1 = ctx->ev[9];
+    CK(cudaEventRecord(t0, ctx->stream));
+    const int64_t U = 3 * P;
+    const int64_t chunk = U > 0 ? ns_pick_chunk(ctx, n, U) : 0;
+    int64_t emit_off = 0;
+    ns_unit_src src;
+    memset(&src, 0, sizeof(src));
+    src.mode = 0;
+    src.n = n;
+    src.counts = d_counts;
+    src.ref = d_ref;
+    for (int64_t u0 = 0; u0 < U; u0 += chunk) {
+        int Uc = (int)((U - u0 < chunk) ? (U - u0) : chunk);
+        rc = ns_run_chunk(ctx, dprm, qtab, src, u0, u0, Uc, out, &emit_off);
+        if (rc)
+            return rc;
+    }
+    CK(cudaEventRecord(t1, ctx->stream));
+    CK(cudaEventSynchronize(t1));
+    ctx->tm.total_ms = ev_ms(t0, t1);
+    ns_finish_out(out, U, emit_off);
+    if (emit_off > out->emit_cap && (out->pvalue || out->gq || out->emit_unit)) {
+        ctx->err = "more emitted units than out->emit_cap";
+        return NS_ERR_EMIT_OVERFLOW;
+    }
+    return NS_OK;
+}
+
+int ns_call_snv(ns_ctx *ctx, const ns_params *prm, int n, int64_t P, const uint8_t *ref, const int32_t *counts,
+                ns_out *out)
+{
+    if (!ctx)
+        return NS_ERR_ARG;
+    if (!prm || !out || n < 1 || P < 0 || (P > 0 && (!ref || !counts))) {
+        ctx->err = "ns_call_snv: bad argument";
+        return NS_ERR_ARG;
+    }
+    CK(cudaSetDevice(ctx->device));
+    ns_reset_out(ctx, out);
+    ns_params dprm;
+    const double *qtab = nullptr;
+    int rc = ns_prepare_params(ctx, prm, n, &dprm, &qtab);
+    if (rc)
+        return rc;
+    cudaEvent_t t0 = ctx->ev[8], t1 = ctx->ev[9];
+    CK(cudaEventRecord(t0, ctx->stream));
+    const int64_t U = 3 * P;
+    const int64_t chunk = U > 0 ? ns_pick_chunk(ctx, n, U) : 0;
+    const int64_t pchunk = chunk / 3;
+    int64_t emit_off = 0;
+    const size_t row_elems = (size_t)9 * n;
+    /* double-buffered staging: the copy stream runs one chunk ahead of the compute stream */
+    auto stage = [&](int64_t p0, int buf) -> int {
+        int64_t pc = (P - p0 < pchunk) ? (P - p0) : pchunk;
+        cudaError_t e;
+        if ((e = ctx->in_counts[buf].reserve((size_t)pc * row_elems)) || (e = ctx->in_ref[buf].reserve((size_t)pc))) {
+            ctx->err = std::string("device allocation (input staging) failed: ") + cudaGetErrorString(e);
+            return NS_ERR_NOMEM;
+        }
+        CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_free[buf], 0));
+        CK(cudaMemcpyAsync(ctx->in_counts[buf].p, counts + (size_t)p0 * row_elems, (size_t)pc * row_elems * sizeof(int32_t),
+                           cudaMemcpyHostToDevice, ctx->copy_stream));
+        CK(cudaMemcpyAsync(ctx->in_ref[buf].p, ref + p0, (size_t)pc, cudaMemcpyHostToDevice, ctx->copy_stream));
+        CK(cudaEventRecord(ctx->ev_h2d[buf], ctx->copy_stream));
+        return NS_OK;
+    };
+    /* the staging buffers start out free */
+    CK(cudaEventRecord(ctx->ev_free[0], ctx->stream));
+    CK(cudaEventRecord(ctx->ev_free[1], ctx->stream));
+    if (P > 0) {
+        rc = stage(0, 0);
+        if (rc)
+            return rc;
+    }
+    int64_t ci = 0;
+    for (int64_t p0 = 0; p0 < P; p0 += pchunk, ci++) {
+        const int buf = (int)(ci & 1);
+        const int64_t pc = (P - p0 < pchunk) ? (P - p0) : pchunk;
+        if (p0 + pchunk < P) {
+            rc = stage(p0 + pchunk, buf ^ 1);
+            if (rc)
+                return rc;
+        }
+        CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_h2d[buf], 0));
+        ns_unit_src src;
+        memset(&src, 0, sizeof(src));
+        src.mode = 0;
+        src.n = n;
+        src.counts = ctx->in_counts[buf].p;
+        src.ref = ctx->in_ref[buf].p;
+        rc = ns_run_chunk(ctx, dprm, qtab, src, 0, 3 * p0, (int)(3 * pc), out, &emit_off);
+        if (rc)
+            return rc;
+        CK(cudaEventRecord(ctx->ev_free[buf], ctx->stream));
+    }
+    CK(cudaEventRecord(t1, ctx->stream));
+    CK(cudaEventSynchronize(t1));
+    ctx->tm.total_ms = ev_ms(t0, t1);
+    ns_finish_out(out, U, emit_off);
+    if (emit_off > out->emit_cap && (out->pvalue || out->gq || out->emit_unit)) {
+        ctx->err = "more emitted units than out->emit_cap";
+        return NS_ERR_EMIT_OVERFLOW;
+    }
+    return NS_OK;
+}
+
+int ns_call_units(ns_ctx *ctx, const ns_params *prm, int n, int64_t U, const int32_t *dp, const int32_t *vp,
+                  const int32_t *vm, const int32_t *rp, const int32_t *rm, const uint8_t *is_indel, int plain,
+                  ns_out *out)
+{
+    if (!ctx)
+        return NS_ERR_ARG;
+    if (!prm || !out || n < 1 || U < 0 || (U > 0 && (!dp || !vp))) {
+        ctx->err = "ns_call_units: bad argument";
+        return NS_ERR_ARG;
+    }
+    CK(cudaSetDevice(ctx->device));
+    ns_reset_out(ctx, out);
+    ns_params dprm;
+    const double *qtab = nullptr;
+    int rc = ns_prepare_params(ctx, prm, n, &dprm, &qtab);
+    if (rc)
+        return rc;
+    cudaEvent_t t0 = ctx->ev[8], t1 = ctx->ev[9];
+    CK(cudaEventRecord(t0, ctx->stream));
+    const int64_t chunk = U > 0 ? ns_pick_chunk(ctx, n, U) : 0;
+    int64_t emit_off = 0;
+    const int32_t *hrows[5] = {dp, vp, vm, rp, rm};
+    for (int64_t u0 = 0; u0 < U; u0 += chunk) {
+        const int Uc = (int)((U - u0 < chunk) ? (U - u0) : chunk);
+        ns_unit_src src;
+        memset(&src, 0, sizeof(src));
+        src.mode = 1;
+        src.n = n;
+        src.plain = plain;
+        const int32_t *drows[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+        for (int k = 0; k < 5; k++) {
+            if (!hrows[k])
+                continue;
+            cudaError_t e = ctx->in_rows[k].reserve((size_t)Uc * n);
+            if (e != cudaSuccess) {
+                ctx->err = std::string("device allocation (unit rows) failed: ") + cudaGetErrorString(e);
+                return NS_ERR_NOMEM;
+            }
+            CK(cudaMemcpyAsync(ctx->in_rows[k].p, hrows[k] + (size_t)u0 * n, (size_t)Uc * n * sizeof(int32_t),
+                               cudaMemcpyHostToDevice, ctx->stream));
+            drows[k] = ctx->in_rows[k].p;
+        }
+        if (is_indel) {
+            cudaError_t e = ctx->in_indel.reserve((size_t)Uc);
+            if (e != cudaSuccess) {
+                ctx->err = std::string("device allocation failed: ") + cudaGetErrorString(e);
+                return NS_ERR_NOMEM;
+            }
+            CK(cudaMemcpyAsync(ctx->in_indel.p, is_indel + u0, (size_t)Uc, cudaMemcpyHostToDevice, ctx->stream));
+            src.is_indel = ctx->in_indel.p;
+        }
+        src.dp = drows[0];
+        src.vp = drows[1];
+        src.vm = drows[2];
+        src.rp = drows[3];
+        src.rm = drows[4];
+        rc = ns_run_chunk(ctx, dprm, qtab, src, 0, u0, Uc, out, &emit_off);
+        if (rc)
+            return rc;
+    }
+    CK(cudaEventRecord(t1, ctx->stream));
+    CK(cudaEventSynchronize(t1));
+    ctx->tm.total_ms = ev_ms(t0, t1);
+    ns_finish_out(out, U, emit_off);
+    if (emit_off > out->emit_cap && (out->pvalue || out->gq || out->emit_unit)) {
+        ctx->err = "more emitted units than out->emit_cap";
+        return NS_ERR_EMIT_OVERFLOW;
+    }
+    return NS_OK;
+}
+
+int ns_glmrob_nb(ns_ctx *ctx, const ns_params *prm, int n, const int32_t *y, const int32_t *x, double *sigma,
+                 double *slope, double *pvalues, double *qvalues, double *gq, int32_t *extra_rob, uint32_t *flags)
+{
+    if (!ctx)
+        return NS_ERR_ARG;
+    if (!prm || !y || !x || n < 1) {
+        ctx->err = "ns_glmrob_nb: bad argument";
+        return NS_ERR_ARG;
+    }
+    ns_params p = *prm;
+    p.emit_mode = NS_EMIT_ALL;
+    p.is_tn = 0;
+    p.output_all_SNVs = 0;
+    ns_out out;
+    memset(&out, 0, sizeof(out));
+    double sg = NAN, sl = NAN;
+    uint32_t fl = 0;
+    out.sigma = &sg;
+    out.slope = &sl;
+    out.flags = &fl;
+    out.emit_cap = 1;
+    out.pvalue = pvalues;
+    out.qvalue = qvalues;
+    out.gq = gq;
+    int rc = ns_call_units(ctx, &p, n, 1, x, y, nullptr, nullptr, nullptr, nullptr, 1, &out);
+    if (rc)
+        return rc;
+    if (sigma)
+        *sigma = sg;
+    if (slope)
+        *slope = sl;
+    if (extra_rob)
+        *extra_rob = (fl & NS_F_EXTRA_ROB) ? 1 : 0;
+    if (flags)
+        *flags = fl;
+    return NS_OK;
+}
+
+} /* extern "C" */

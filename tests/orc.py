@@ -192,6 +192,8 @@ def call_snv_batch(ref, counts, prm, n_threads=1):
     out["gate2"] = np.array([info[u].gate2 for u in range(U)], dtype=np.int32)
     out["max_gq"] = np.array([info[u].max_gq for u in range(U)])
     out["n_outer"] = np.array([info[u].glm.n_outer for u in range(U)], dtype=np.int32)
+    out["maxit_hit"] = np.array([info[u].glm.maxit_hit for u in range(U)], dtype=np.int32)
+    out["quad_error"] = np.array([info[u].glm.quad_error for u in range(U)], dtype=np.int32)
     out["n_seed"] = np.array([info[u].glm.n_seed for u in range(U)], dtype=np.int64)
     out["n_lattice"] = np.array([info[u].glm.n_lattice for u in range(U)], dtype=np.int64)
     out["n_quad"] = np.array([info[u].glm.n_quad for u in range(U)], dtype=np.int64)

@@ -7,6 +7,9 @@ import numpy as np
 from needlestack_b200 import _abi
 
 TOL = 1e-6
+# sigma is the root of a Brent search that the reference stops at an ABSOLUTE precision
+# sig.prec = 1e-8 (glm_rob_nb.r:17,176): two correct runs may differ by that much.
+SIGMA_ABS = 2e-8
 
 
 def snv_unit_rows(ref, counts, u):
@@ -68,7 +71,7 @@ def compare(O, R, units=None, tol=TOL, gq_thr=50.0, label=""):
     units = range(U) if units is None else units
     rep = dict(n_units=0, n_fitted=0, max_rel_sigma=0.0, max_rel_slope=0.0, max_d_gq=0.0, max_d_qval=0.0,
                max_d_p=0.0, max_d_sb=0.0, gt_mismatch=0, status_mismatch=0, gate_mismatch=0, iter_mismatch=0,
-               near_threshold=0, bad=[])
+               near_threshold=0, nonconverged=0, bad=[])
     for u in units:
         rep["n_units"] += 1
         fl = int(R["flags"][u])
@@ -80,9 +83,20 @@ def compare(O, R, units=None, tol=TOL, gq_thr=50.0, label=""):
             continue
         if fl & _abi.NS_F_SKIPPED:
             continue
+        if not gated_r and "maxit_hit" in O and O["maxit_hit"][u]:
+            # the reference's loop stopped on maxit (glm_rob_nb.r:171): the iterates did not settle,
+            # ulp-level differences are amplified; such units are counted, flagged and required to
+            # be flagged MAXIT on the GPU too, but not compared numerically
+            rep["n_fitted"] += 1
+            rep["nonconverged"] += 1
+            if not (fl & _abi.NS_F_MAXIT):
+                rep["bad"].append((u, "oracle hit maxit, GPU did not"))
+            continue
         if not gated_r:
             rep["n_fitted"] += 1
             ds = abs(R["sigma"][u] - O["sigma"][u]) / abs(O["sigma"][u])
+            if abs(R["sigma"][u] - O["sigma"][u]) <= SIGMA_ABS:
+                ds = min(ds, tol)
             dl = abs(R["slope"][u] - O["slope"][u]) / abs(O["slope"][u])
             rep["max_rel_sigma"] = max(rep["max_rel_sigma"], ds)
             rep["max_rel_slope"] = max(rep["max_rel_slope"], dl)

@@ -1,0 +1,71 @@
+"""CUDA path (through the C ABI) against the CPU oracle on the same seeded inputs."""
+import numpy as np
+import pytest
+
+import parity
+from needlestack_b200 import NS_EMIT_ALL, make_params, synth
+
+pytestmark = pytest.mark.gpu
+
+
+def _gpu_dict(R):
+    out = {k: R.dense(k) for k in ("pvalue", "qvalue", "gq", "qval_minaf", "sor", "rvsb", "fs")}
+    out["gt"] = R.dense("gt", fill=0)
+    out["status"] = R.dense("status", fill=0)
+    out["pooled"] = R.dense("pooled")
+    for k in ("sigma", "slope", "max_gq", "flags", "n_outer", "n_irls", "n_obj"):
+        out[k] = R[k]
+    return out
+
+
+def _run(caller, oracle, cfgname, P, seed, pairs=None, pv=1e-3, pg=1e-4, threads=8, **kw):
+    cfg = synth.CONFIGS[cfgname]
+    ref, counts = synth.generate(cfg, P=P, seed=seed, p_variant=pv, p_germline=pg)
+    O = oracle.call_snv_batch(ref, np.ascontiguousarray(counts.transpose(1, 0, 2)),
+                              oracle.call_params(pairs=pairs, **kw), n_threads=threads)
+    R = caller.call_snv(ref, counts, prm=make_params(pairs=pairs, emit_mode=NS_EMIT_ALL, **kw))
+    rep = parity.compare(O, _gpu_dict(R), label=cfgname)
+    assert rep["n_fitted"] == R.n_fitted
+    return rep, R
+
+
+def test_c1_shape(caller, oracle):
+    rep, R = _run(caller, oracle, "C1", 3000, 11, pv=0.01, pg=0.003)
+    assert rep["n_fitted"] > 300
+
+
+def test_c2_shape(caller, oracle):
+    rep, R = _run(caller, oracle, "C2", 1500, 12, pv=0.01, pg=0.003)
+    assert rep["n_fitted"] > 200
+
+
+def test_extra_robust(caller, oracle):
+    rep, R = _run(caller, oracle, "C1", 2000, 13, pv=0.02, pg=0.03, extra_rob=1)
+    assert (R.flags & 2).sum() > 0
+
+
+def test_tn_pairs(caller, oracle):
+    cfg = synth.CONFIGS["C4"]
+    rep, R = _run(caller, oracle, "C4", 60, 14, pairs=synth.tn_pairs(cfg), pv=0.05, pg=0.05)
+    assert rep["n_fitted"] > 20
+
+
+def test_deep_c3_shape(caller, oracle):
+    rep, R = _run(caller, oracle, "C3", 12, 15, pv=0.1, pg=0.0)
+    assert R.n_quad > 0  # the spline + dqags path ran
+
+
+def test_output_all_and_binomial_power(caller, oracle):
+    _run(caller, oracle, "C1", 500, 16, pv=0.02, pg=0.01, output_all_SNVs=1, afmin_power=0.05)
+
+
+def test_skipped_reference_base_and_chunking(caller, oracle, monkeypatch):
+    cfg = synth.CONFIGS["C1"]
+    ref, counts = synth.generate(cfg, P=700, seed=17, p_variant=0.02)
+    ref[::7] = 4  # 'N' reference: needlestack.r:319 skips the position
+    O = oracle.call_snv_batch(ref, np.ascontiguousarray(counts.transpose(1, 0, 2)), oracle.call_params())
+    R = caller.call_snv(ref, counts, prm=make_params(emit_mode=NS_EMIT_ALL))
+    d = _gpu_dict(R)
+    parity.compare(O, d, label="skipped")
+    assert R.n_skipped == 3 * len(ref[::7])
+    assert np.all(R.emit_index[np.repeat(ref > 3, 3)] == -1)
