@@ -326,7 +326,8 @@ def main():
 
     # ---- rooflines (rank 0's kernels) ----
     fit_s = tm_sum["fit_ms"] * 1e-3
-    flops = 400.0 * seeds + 32.0 * lattice + 2000.0 * quad
+    fseeds, flattice = tm_sum["fast_seed"], tm_sum["fast_lattice"]
+    flops = 400.0 * fseeds + 32.0 * flattice
     ach = flops / fit_s / 1e12 if fit_s > 0 else 0.0
     peaks = {}
     try:
@@ -341,8 +342,10 @@ def main():
     roofline = {"kernel": "k_fit", "bound": "fp64", "achieved": ach, "peak": fp64_peak, "unit": "TFLOP/s",
                 "frac": ach / fp64_peak if fp64_peak else None, "traffic": None,
                 "peak_source": "DFMA micro-benchmark run in this process (MEASURED_PEAKS.json has no FP64 entry)",
-                "flops_model": "400*N_seed + 32*N_lattice + 2000*N_quad (SURVEY.md 8d); counters from the kernel",
-                "n_seed": seeds, "n_lattice": lattice, "n_quad": quad,
+                "flops_model": "400*N_seed + 32*N_lattice (+ 2000*N_quad, zero in this kernel) (SURVEY.md 8d); "
+                               "counters from the kernel",
+                "n_seed": fseeds, "n_lattice": flattice, "all_kernels": {"n_seed": seeds, "n_lattice": lattice,
+                                                                       "n_quad": quad},
                 "share_of_step": tm_sum["fit_ms"] / ms if ms else None}
     roofline_gate = {"kernel": "k_gate", "bound": "hbm", "achieved": gate_ach, "peak": hbm_peak, "unit": "GB/s",
                      "frac": gate_ach / hbm_peak, "traffic": None, "peak_source": hbm_src,

@@ -120,8 +120,12 @@ typedef struct ns_out {
 
 /* per-call device timings of the last ns_call_* on this context, milliseconds */
 typedef struct ns_timings {
-    double h2d_ms, gate_ms, fit_ms, post_ms, pack_ms, d2h_ms, total_ms;
+    double h2d_ms, gate_ms, fit_ms, heavy_ms, post_ms, pack_ms, d2h_ms, total_ms;
+    double heavy_pre_ms; /* CTA-per-unit kernel on its own stream, concurrent with fit_ms */
+    double fit_phase_ms; /* wall time of the whole fit phase (both streams) */
     int64_t kernel_launches;
+    int64_t n_heavy; /* units that took the spline + quadrature kernel */
+    uint64_t fast_seed, fast_lattice; /* work counters of the warp kernel alone (k_fit) */
 } ns_timings;
 
 typedef struct ns_ctx ns_ctx;

@@ -8,11 +8,11 @@ ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libns_b200.so")
-SOURCES = [os.path.join(CSRC, "ns_api.cu")]
-DEPS = SOURCES + [os.path.join(CSRC, f) for f in ("ns_math.cuh", "ns_quad.cuh", "ns_core.cuh")] + [
+SOURCES = [os.path.join(CSRC, f) for f in ("ns_api.cu", "ns_k_gate.cu", "ns_k_fit.cu", "ns_k_post.cu")]
+DEPS = SOURCES + [os.path.join(CSRC, f) for f in ("ns_math.cuh", "ns_quad.cuh", "ns_core.cuh", "ns_fit.cuh", "ns_kernels.cuh", "ns_coop.cuh")] + [
     os.path.join(ROOT, "include", "ns_b200.h")]
-NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-shared",
-              "-Xcompiler", "-fPIC"]
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC"]
+OBJDIR = os.path.join(HERE, "build")
 
 
 def stale():
@@ -23,17 +23,39 @@ def stale():
 
 
 def build(force=False, verbose=False):
+    """one nvcc -c per translation unit, in parallel, then one link; objects are cached by mtime"""
     if not force and not stale():
         return LIB
     nvcc = os.environ.get("NVCC", "nvcc")
     os.makedirs(LIBDIR, exist_ok=True)
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + SOURCES
-    r = subprocess.run(cmd, capture_output=True, text=True)
+    os.makedirs(OBJDIR, exist_ok=True)
+    headers = [d for d in DEPS if d not in SOURCES]
+    hmt = max(os.path.getmtime(h) for h in headers)
+    procs, objs = [], []
+    for src in SOURCES:
+        obj = os.path.join(OBJDIR, os.path.basename(src)[:-3] + ".o")
+        objs.append(obj)
+        if not force and os.path.exists(obj) and os.path.getmtime(obj) > max(hmt, os.path.getmtime(src)):
+            continue
+        cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", "-o", obj, src]
+        procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+    failed = False
+    for src, p in procs:
+        out, _ = p.communicate()
+        if p.returncode != 0:
+            failed = True
+            sys.stderr.write(out)
+        elif verbose:
+            sys.stderr.write(out)
+    if failed:
+        raise RuntimeError("nvcc failed building libns_b200.so")
+    tmp = LIB + ".tmp"
+    r = subprocess.run([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", tmp] + objs,
+                       capture_output=True, text=True)
     if r.returncode != 0:
         sys.stderr.write(r.stdout + r.stderr)
-        raise RuntimeError("nvcc failed building libns_b200.so")
-    if verbose:
-        sys.stderr.write(r.stderr)
+        raise RuntimeError("link of libns_b200.so failed")
+    os.replace(tmp, LIB)
     return LIB
 
 

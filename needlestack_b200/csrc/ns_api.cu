@@ -20,238 +20,7 @@
 #include <string>
 #include <vector>
 
-#include "ns_core.cuh"
-
-#define NS_WPB_GATE 8
-#define NS_QTAB_LEN 65536
-
-/* ---- device-side bookkeeping ------------------------------------------------------- */
-struct ns_counters {
-    int n_fit, n_post, n_rows, n_emit;
-    int next_fit, next_post, pad0, pad1;
-    unsigned long long n_seed, n_lattice, n_quad, pad2;
-};
-
-struct ns_planes {
-    double *pvalue, *qvalue, *gq, *qval_minaf, *sor, *rvsb, *fs, *pooled;
-    uint8_t *gt, *status;
-};
-
-struct ns_unit_arrays {
-    uint32_t *flags, *iters;
-    unsigned long long *cycles;
-    double *sigma, *slope, *max_gq;
-    int *needrow, *row, *emitflag, *emitidx;
-    int *fit_list, *post_list;
-};
-
-extern __shared__ double ns_smem[];
-
-__global__ void __launch_bounds__(NS_WPB_GATE * 32)
-k_gate(ns_unit_src src, ns_params prm, int64_t u0, int n_units, ns_unit_arrays ua, ns_counters *cnt)
-{
-    const int n = src.n;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    double *scratch = ns_smem + (size_t)warp * (size_t)n;
-    const int wstride = gridDim.x * NS_WPB_GATE;
-    const bool emit_all = prm.emit_mode == NS_EMIT_ALL;
-    for (int u = blockIdx.x * NS_WPB_GATE + warp; u < n_units; u += wstride) {
-        ns_rows r = ns_unit_rows(src, u0 + u);
-        uint32_t flags = ns_gate_unit<WarpG>(r, n, prm, src.plain, scratch);
-        if (lane == 0) {
-            const bool gated = flags & NS_F_GATED, skipped = flags & NS_F_SKIPPED;
-            const bool out_all = (!r.is_indel) && prm.output_all_SNVs;
-            const bool need = !skipped && (!gated || emit_all || out_all);
-            ua.flags[u] = flags;
-            ua.sigma[u] = NAN;
-            ua.slope[u] = NAN;
-            ua.max_gq[u] = 0.0;
-            ua.iters[u] = 0;
-            ua.cycles[u] = 0;
-            ua.needrow[u] = need;
-            ua.emitflag[u] = 0;
-            if (!gated)
-                ua.fit_list[atomicAdd(&cnt->n_fit, 1)] = u;
-            if (need)
-                ua.post_list[atomicAdd(&cnt->n_post, 1)] = u;
-        }
-    }
-}
-
-__global__ void k_fit(ns_unit_src src, ns_params prm, int64_t u0, ns_unit_arrays ua, ns_counters *cnt)
-{
-    const int n = src.n;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    ns_work w;
-    ns_work_bind(w, ns_smem + (size_t)warp * ns_work_doubles(n), n);
-    unsigned long long tot_seed = 0, tot_lat = 0, tot_quad = 0;
-    const int n_fit = cnt->n_fit;
-    for (;;) {
-        int idx = 0;
-        if (lane == 0)
-            idx = atomicAdd(&cnt->next_fit, 1);
-        idx = __shfl_sync(0xffffffffu, idx, 0);
-        if (idx >= n_fit)
-            break;
-        const int u = ua.fit_list[idx];
-        const long long t_start = clock64();
-        const uint32_t flags = ua.flags[u];
-        ns_rows r = ns_unit_rows(src, u0 + u);
-        const bool inv = flags & NS_F_REF_INV, extra = flags & NS_F_EXTRA_ROB;
-        double maxmu = -INFINITY;
-        for (int i = lane; i < n; i += 32) {
-            double x = ns_ld(r.dp, i);
-            double y = inv ? ns_ld(r.rp, i) + ns_ld(r.rm, i) : ns_ld(r.vp, i) + ns_ld(r.vm, i);
-            maxmu = fmax(maxmu, x);
-            bool keep = !(extra && y / x > prm.min_af_extra_rob);
-            w.y[i] = y;
-            w.x[i] = keep ? x : 0.0;
-        }
-        maxmu = WarpG::max(maxmu);
-        __syncwarp();
-        ns_fit_result res;
-        ns_fit_unit<WarpG>(w, n, maxmu, prm, res);
-        tot_seed += res.cnt.n_seed;
-        tot_lat += res.cnt.n_lattice;
-        tot_quad += res.cnt.n_quad;
-        if (lane == 0) {
-            ua.sigma[u] = res.sigma;
-            ua.slope[u] = res.slope;
-            ua.flags[u] = flags | res.flags;
-            unsigned no = res.n_outer > 255 ? 255 : res.n_outer, ni = res.n_irls > 1023 ? 1023 : res.n_irls,
-                     nj = res.n_obj > 16383 ? 16383 : res.n_obj;
-            ua.iters[u] = no | (ni << 8) | (nj << 18);
-            ua.cycles[u] = (unsigned long long)(clock64() - t_start);
-        }
-        __syncwarp();
-    }
-    /* per-lane counters -> warp -> global */
-    for (int o = 16; o > 0; o >>= 1) {
-        tot_seed += __shfl_xor_sync(0xffffffffu, tot_seed, o);
-        tot_lat += __shfl_xor_sync(0xffffffffu, tot_lat, o);
-        tot_quad += __shfl_xor_sync(0xffffffffu, tot_quad, o);
-    }
-    if (lane == 0 && (tot_seed | tot_lat | tot_quad)) {
-        atomicAdd(&cnt->n_seed, tot_seed);
-        atomicAdd(&cnt->n_lattice, tot_lat);
-        atomicAdd(&cnt->n_quad, tot_quad);
-    }
-}
-
-__global__ void k_post(ns_unit_src src, ns_params prm, int64_t u0, ns_unit_arrays ua, ns_planes pl,
-                       const double *qtab, int qtab_len, ns_counters *cnt)
-{
-    const int n = src.n;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    double *sm = ns_smem + (size_t)warp * (3 * (size_t)n + 8);
-    const int n_post = cnt->n_post;
-    for (;;) {
-        int idx = 0;
-        if (lane == 0)
-            idx = atomicAdd(&cnt->next_post, 1);
-        idx = __shfl_sync(0xffffffffu, idx, 0);
-        if (idx >= n_post)
-            break;
-        const int u = ua.post_list[idx];
-        const size_t row = (size_t)ua.row[u];
-        ns_rows r = ns_unit_rows(src, u0 + u);
-        ns_unit_out o;
-        o.pvalue = pl.pvalue + row * n;
-        o.qvalue = pl.qvalue + row * n;
-        o.gq = pl.gq + row * n;
-        o.qval_minaf = pl.qval_minaf + row * n;
-        o.sor = pl.sor + row * n;
-        o.rvsb = pl.rvsb + row * n;
-        o.fs = pl.fs + row * n;
-        o.gt = pl.gt + row * n;
-        o.status = pl.status + row * n;
-        o.pooled = pl.pooled + row * 8;
-        if (lane < 8)
-            o.pooled[lane] = NAN;
-        double mg = 0;
-        uint32_t flags = ns_post_unit<WarpG>(r, n, prm, ua.flags[u], ua.sigma[u], ua.slope[u], qtab, qtab_len,
-                                             o, sm, mg);
-        if (lane == 0) {
-            ua.flags[u] = flags;
-            ua.max_gq[u] = mg;
-            bool emit = prm.emit_mode == NS_EMIT_ALL || (prm.emit_mode == NS_EMIT_FITTED && !(flags & NS_F_GATED)) ||
-                        (flags & NS_F_GATE2);
-            ua.emitflag[u] = emit;
-        }
-        __syncwarp();
-    }
-}
-
-__global__ void k_scan_total(const int *flag, const int *excl, int n, int *total)
-{
-    if (threadIdx.x == 0 && blockIdx.x == 0)
-        *total = n > 0 ? excl[n - 1] + flag[n - 1] : 0;
-}
-
-/* rows of emitted units, in unit order, into the packed planes */
-__global__ void k_pack(int n, int n_units, int64_t u0, int64_t emit_off, int cap, ns_unit_arrays ua,
-                       ns_planes src, ns_planes dst, int64_t *emit_unit, int *emit_index_out)
-{
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int wpb = blockDim.x >> 5;
-    for (int u = blockIdx.x * wpb + warp; u < n_units; u += gridDim.x * wpb) {
-        if (!ua.emitflag[u]) {
-            if (lane == 0)
-                emit_index_out[u] = -1;
-            continue;
-        }
-        const int d = ua.emitidx[u];
-        if (lane == 0)
-            emit_index_out[u] = (int)(emit_off + d);
-        if (d >= cap)
-            continue;
-        const size_t so = (size_t)ua.row[u] * n, dof = (size_t)d * n;
-        for (int i = lane; i < n; i += 32) {
-            dst.pvalue[dof + i] = src.pvalue[so + i];
-            dst.qvalue[dof + i] = src.qvalue[so + i];
-            dst.gq[dof + i] = src.gq[so + i];
-            dst.qval_minaf[dof + i] = src.qval_minaf[so + i];
-            dst.sor[dof + i] = src.sor[so + i];
-            dst.rvsb[dof + i] = src.rvsb[so + i];
-            dst.fs[dof + i] = src.fs[so + i];
-            dst.gt[dof + i] = src.gt[so + i];
-            dst.status[dof + i] = src.status[so + i];
-        }
-        if (lane < 8)
-            dst.pooled[(size_t)d * 8 + lane] = src.pooled[(size_t)ua.row[u] * 8 + lane];
-        if (lane == 0)
-            emit_unit[d] = u0 + u;
-    }
-}
-
-/* y* tables of toQvalueN / toQvalueT (needlestack.r:243,249): they depend on the depth only */
-__global__ void k_qtab(double *tabN, double *tabT, int len, double sigma_normal, double afmin)
-{
-    int x = blockIdx.x * blockDim.x + threadIdx.x;
-    if (x >= len)
-        return;
-    tabN[x] = ns_qnbinom_mu(0.01, 1 / sigma_normal, 0.5 * (double)x);
-    if (tabT)
-        tabT[x] = (afmin >= 0) ? ns_qbinom(0.01, (double)x, afmin) : 0.0;
-}
-
-/* DFMA throughput probe: 8 independent chains per thread */
-__global__ void k_dfma(double *out, int iters, double a, double b)
-{
-    double x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6,
-           x7 = x0 + 7;
-    for (int i = 0; i < iters; i++) {
-        x0 = fma(x0, a, b);
-        x1 = fma(x1, a, b);
-        x2 = fma(x2, a, b);
-        x3 = fma(x3, a, b);
-        x4 = fma(x4, a, b);
-        x5 = fma(x5, a, b);
-        x6 = fma(x6, a, b);
-        x7 = fma(x7, a, b);
-    }
-    out[blockIdx.x * blockDim.x + threadIdx.x] = x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7;
-}
+#include "ns_kernels.cuh"
 
 /* ---- host side ----------------------------------------------------------------------- */
 template <class T> struct DevBuf {
@@ -308,7 +77,8 @@ struct PlaneSet {
 struct ns_ctx {
     int device = 0;
     int sm_count = 148;
-    cudaStream_t stream = nullptr, own_stream = nullptr, copy_stream = nullptr;
+    cudaStream_t stream = nullptr, own_stream = nullptr, copy_stream = nullptr, heavy_stream = nullptr;
+    cudaEvent_t ev_fork, ev_join, ev_h0, ev_h1;
     std::string err;
     /* staging of host inputs, double buffered */
     DevBuf<int32_t> in_counts[2];
@@ -320,7 +90,7 @@ struct ns_ctx {
     DevBuf<uint32_t> flags, iters;
     DevBuf<unsigned long long> cycles;
     DevBuf<double> sigma, slope, max_gq;
-    DevBuf<int> needrow, row, emitflag, emitidx, fit_list, post_list, emit_index_out;
+    DevBuf<int> needrow, row, emitflag, emitidx, fit_list, post_list, heavy_list, pre_list, emit_index_out;
     DevBuf<int64_t> emit_unit;
     DevBuf<ns_counters> counters;
     DevBuf<unsigned char> cub_tmp;
@@ -417,7 +187,11 @@ ns_ctx *ns_create(int device, char *err, size_t errlen)
     ctx->device = device;
     ctx->sm_count = prop.multiProcessorCount;
     bool ok = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) == cudaSuccess &&
-              cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) == cudaSuccess;
+              cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) == cudaSuccess &&
+              cudaStreamCreateWithFlags(&ctx->heavy_stream, cudaStreamNonBlocking) == cudaSuccess &&
+              cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming) == cudaSuccess &&
+              cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming) == cudaSuccess &&
+              cudaEventCreate(&ctx->ev_h0) == cudaSuccess && cudaEventCreate(&ctx->ev_h1) == cudaSuccess;
     for (int i = 0; i < 2 && ok; i++)
         ok = cudaEventCreateWithFlags(&ctx->ev_h2d[i], cudaEventDisableTiming) == cudaSuccess &&
              cudaEventCreateWithFlags(&ctx->ev_free[i], cudaEventDisableTiming) == cudaSuccess;
@@ -456,7 +230,7 @@ void ns_destroy(ns_ctx *ctx)
     ctx->in_indel.release();
     ctx->flags.release(), ctx->iters.release(), ctx->cycles.release(), ctx->sigma.release(), ctx->slope.release(), ctx->max_gq.release();
     ctx->needrow.release(), ctx->row.release(), ctx->emitflag.release(), ctx->emitidx.release();
-    ctx->fit_list.release(), ctx->post_list.release(), ctx->emit_index_out.release(), ctx->emit_unit.release();
+    ctx->fit_list.release(), ctx->post_list.release(), ctx->heavy_list.release(), ctx->pre_list.release(), ctx->emit_index_out.release(), ctx->emit_unit.release();
     ctx->counters.release(), ctx->cub_tmp.release(), ctx->rows.release(), ctx->packed.release();
     ctx->pair_idx.release(), ctx->role.release(), ctx->qtabN.release(), ctx->qtabT.release();
     for (int i = 0; i < 10; i++)
@@ -465,6 +239,8 @@ void ns_destroy(ns_ctx *ctx)
         cudaFreeHost(ctx->h_counters);
     cudaStreamDestroy(ctx->own_stream);
     cudaStreamDestroy(ctx->copy_stream);
+    cudaStreamDestroy(ctx->heavy_stream);
+    cudaEventDestroy(ctx->ev_fork), cudaEventDestroy(ctx->ev_join), cudaEventDestroy(ctx->ev_h0), cudaEventDestroy(ctx->ev_h1);
     delete ctx;
 }
 
@@ -604,7 +380,7 @@ static cudaError_t ns_reserve_units(ns_ctx *ctx, size_t U)
     if ((e = ctx->flags.reserve(U)) || (e = ctx->iters.reserve(U)) || (e = ctx->cycles.reserve(U)) || (e = ctx->sigma.reserve(U)) ||
         (e = ctx->slope.reserve(U)) || (e = ctx->max_gq.reserve(U)) || (e = ctx->needrow.reserve(U)) ||
         (e = ctx->row.reserve(U)) || (e = ctx->emitflag.reserve(U)) || (e = ctx->emitidx.reserve(U)) ||
-        (e = ctx->fit_list.reserve(U)) || (e = ctx->post_list.reserve(U)) || (e = ctx->emit_index_out.reserve(U)))
+        (e = ctx->fit_list.reserve(U)) || (e = ctx->post_list.reserve(U)) || (e = ctx->heavy_list.reserve(U)) || (e = ctx->pre_list.reserve(U)) || (e = ctx->emit_index_out.reserve(U)))
         return e;
     size_t tmp = 0;
     cub::DeviceScan::ExclusiveSum(nullptr, tmp, (int *)nullptr, (int *)nullptr, (int)U);
@@ -630,7 +406,7 @@ static int ns_run_chunk(ns_ctx *ctx, const ns_params &dprm, const double *qtab, 
         return NS_ERR_NOMEM;
     }
     ns_unit_arrays ua = {ctx->flags.p,    ctx->iters.p,    ctx->cycles.p,   ctx->sigma.p,   ctx->slope.p,    ctx->max_gq.p,  ctx->needrow.p,
-                         ctx->row.p,      ctx->emitflag.p, ctx->emitidx.p, ctx->fit_list.p, ctx->post_list.p};
+                         ctx->row.p,      ctx->emitflag.p, ctx->emitidx.p, ctx->fit_list.p, ctx->post_list.p, ctx->heavy_list.p, ctx->pre_list.p};
     CK(cudaMemsetAsync(ctx->counters.p, 0, sizeof(ns_counters), st));
     /* gate */
     CK(cudaEventRecord(ctx->ev[0], st));
@@ -660,16 +436,39 @@ static int ns_run_chunk(ns_ctx *ctx, const ns_params &dprm, const double *qtab, 
         ctx->err = std::string("device allocation (result planes) failed: ") + cudaGetErrorString(ce);
         return NS_ERR_NOMEM;
     }
-    /* fit */
+    /* fit: the CTA-per-unit kernel for the units predicted heavy runs on its own stream next to
+     * the persistent warp kernel; units the warp kernel hands over later get a second pass */
+    const int n_pre = ctx->h_counters->n_pre, n_light = ctx->h_counters->n_light;
+    const int hthreads = NS_HEAVY_THREADS;
+    const size_t smh = (NS_RTAB_HEAVY + ns_work_doubles(n) + (size_t)(hthreads / 32) * NS_COOP_DOUBLES) * sizeof(double);
     CK(cudaEventRecord(ctx->ev[2], st));
+    bool heavy_forked = false;
     if (n_fit > 0) {
-        int wpb = 4;
+        if (smh > 227 * 1024) {
+            ctx->err = "too many samples for the heavy kernel's working set";
+            return NS_ERR_ARG;
+        }
+        if (smh > 48 * 1024)
+            CK(cudaFuncSetAttribute(k_fit_heavy, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smh));
+    }
+    if (n_pre > 0) {
+        CK(cudaEventRecord(ctx->ev_fork, st));
+        CK(cudaStreamWaitEvent(ctx->heavy_stream, ctx->ev_fork, 0));
+        CK(cudaEventRecord(ctx->ev_h0, ctx->heavy_stream));
+        int hblocks = n_pre < ctx->sm_count ? n_pre : ctx->sm_count;
+        k_fit_heavy<<<hblocks, hthreads, smh, ctx->heavy_stream>>>(src, dprm, u0_src, ua, ctx->counters.p, 0);
+        CK(cudaGetLastError());
+        CK(cudaEventRecord(ctx->ev_h1, ctx->heavy_stream));
+        CK(cudaEventRecord(ctx->ev_join, ctx->heavy_stream));
+        heavy_forked = true;
+        ctx->tm.kernel_launches++;
+    }
+    if (n_light > 0) {
+        const int wpb = 4;
         size_t per_warp = ns_work_doubles(n) * sizeof(double);
-        while (wpb > 1 && wpb * per_warp > 200 * 1024)
-            wpb >>= 1;
-        size_t sm = wpb * per_warp;
+        size_t sm = NS_RTAB * sizeof(double) + wpb * per_warp;
         if (sm > 227 * 1024) {
-            ctx->err = "too many samples for the on-chip working set (n > ~4700)";
+            ctx->err = "too many samples for the on-chip working set (n > ~1100)";
             return NS_ERR_ARG;
         }
         if (sm > 48 * 1024)
@@ -679,10 +478,20 @@ static int ns_run_chunk(ns_ctx *ctx, const ns_params &dprm, const double *qtab, 
         if (bps < 1)
             bps = 1;
         int blocks = ctx->sm_count * bps;
-        int need = (n_fit + wpb - 1) / wpb;
+        int need = (n_light + wpb - 1) / wpb;
         if (blocks > need)
             blocks = need;
         k_fit<<<blocks, wpb * 32, sm, st>>>(src, dprm, u0_src, ua, ctx->counters.p);
+        CK(cudaGetLastError());
+        ctx->tm.kernel_launches++;
+    }
+    CK(cudaEventRecord(ctx->ev[7], st));
+    if (heavy_forked)
+        CK(cudaStreamWaitEvent(st, ctx->ev_join, 0));
+    if (n_light > 0) {
+        /* handed over by the warp kernel (count is on the device: a few CTAs that exit at once if none) */
+        int hblocks = n_light < ctx->sm_count ? n_light : ctx->sm_count;
+        k_fit_heavy<<<hblocks, hthreads, smh, st>>>(src, dprm, u0_src, ua, ctx->counters.p, 1);
         CK(cudaGetLastError());
         ctx->tm.kernel_launches++;
     }
@@ -779,7 +588,14 @@ static int ns_run_chunk(ns_ctx *ctx, const ns_params &dprm, const double *qtab, 
     CK(cudaEventRecord(ctx->ev[6], st));
     CK(cudaStreamSynchronize(st));
     ctx->tm.gate_ms += ev_ms(ctx->ev[0], ctx->ev[1]);
-    ctx->tm.fit_ms += ev_ms(ctx->ev[2], ctx->ev[3]);
+    ctx->tm.fit_ms += ev_ms(ctx->ev[2], ctx->ev[7]);
+    ctx->tm.heavy_ms += ev_ms(ctx->ev[7], ctx->ev[3]);
+    if (heavy_forked)
+        ctx->tm.heavy_pre_ms += ev_ms(ctx->ev_h0, ctx->ev_h1);
+    ctx->tm.fit_phase_ms += ev_ms(ctx->ev[2], ctx->ev[3]);
+    ctx->tm.n_heavy += ctx->h_counters->n_heavy + ctx->h_counters->n_pre;
+    ctx->tm.fast_seed += ctx->h_counters->fast_seed;
+    ctx->tm.fast_lattice += ctx->h_counters->fast_lattice;
     ctx->tm.post_ms += ev_ms(ctx->ev[3], ctx->ev[4]);
     ctx->tm.pack_ms += ev_ms(ctx->ev[4], ctx->ev[5]);
     ctx->tm.d2h_ms += ev_ms(ctx->ev[5], ctx->ev[6]);

@@ -1,0 +1,767 @@
+/*
+ * ns_fit.cuh — the robust negative-binomial regression of one unit
+ * (/root/reference/bin/glm_rob_nb.r:58-205), for a group of lanes G.
+ *
+ * Two code paths compute the same estimator:
+ *   FAST = true   what the persistent warp kernel k_fit runs.  A window that starts at 0 and
+ *                 is shorter than NS_JTAB lattice points (every sample at exome depth) is
+ *                 summed with division-free recurrences: the negative-binomial pmf from
+ *                 pmf(0) = exp(-size*log(1+sig*mu)), the digamma difference
+ *                 digamma(j+1/sig) - digamma(1/sig) = sum_{k<j} 1/(1/sig+k) from a per-sigma
+ *                 table the warp builds once per objective evaluation, 1/(j+1) from a table.
+ *                 Longer windows use the generic lattice sum; a unit that needs the spline +
+ *                 quadrature branch (window > 2*n_ai.sig.tukey) is handed to the heavy kernel.
+ *   FAST = false  the generic path: Loader pmf seeds, spline + QUADPACK dqags
+ *                 (glm_rob_nb.r:115-118,131-134,151-154); run by k_fit_heavy with one CTA per
+ *                 unit (BlockG), and by the serial emulation in tests/.
+ */
+#pragma once
+#include "ns_math.cuh"
+#include "ns_quad.cuh"
+
+#define NS_JTAB 64  /* digamma-difference table entries per sigma */
+#define NS_RTAB 256 /* reciprocals 1/j, j = 1..255 */
+#define NS_STEP_BY 16.0 /* knot spacing up to which the spline knots are reached by lattice recurrence */
+
+struct ns_fit_counters {
+    unsigned long long n_seed, n_lattice, n_quad;
+    int quad_err;      /* an integrate() that R would have raised as an error */
+    int quad_overflow; /* on-chip subdivision list exhausted */
+};
+
+NS_HD double ns_varfunc(double mu, double sig) { return mu + sig * (mu * mu); } /* :73 */
+
+NS_HD double ns_tukeypsi(double r, double c)
+{ /* glm_rob_nb.r:106-108 */
+    if (r != r)
+        return r;
+    if (fabs(r) > c)
+        return 0.0;
+    double t = (r / c) * (r / c) - 1;
+    return t * t * r;
+}
+
+/* ---- generic window expectations ----------------------------------------------------- */
+/* lattice-sum branch of ai.sig.tukey (glm_rob_nb.r:155-158) */
+NS_GF inline double ns_ai_sum(double mui, double sig, double c, double j1, double j2, double dg0)
+{
+    const double sqrtV = sqrt(mui * (sig * mui + 1));
+    const double invsig = 1 / sig;
+    const double lg = log(mui / invsig + 1);
+    const double csd = c * sqrtV, mpi = mui + invsig;
+    double pm = ns_dnbinom_mu(j1, invsig, mui);
+    double D = (j1 == 0) ? 0.0 : ns_digamma(j1 + invsig) - dg0; /* digamma(j+1/sig)-digamma(1/sig) */
+    const double q = mui / (mui + invsig);
+    double acc = 0;
+    for (double j = j1; j <= j2; j += 1) {
+        double d = j - mui;
+        double t = d / csd;
+        double w = (t * t - 1) * (t * t - 1);
+        double psi = D - lg - d / mpi;
+        acc += w * psi * pm;
+        double ja = j + invsig, jb = j + 1;
+        double rr = 1.0 / (ja * jb);
+        pm *= (ja * ja) * rr * q; /* pmf(j+1)/pmf(j) = (j+size)/(j+1) * mu/(mu+size) */
+        D += jb * rr;             /* digamma(x+1) = digamma(x) + 1/x */
+    }
+    return acc;
+}
+
+/* spline + quadrature branch of ai.sig.tukey (glm_rob_nb.r:151-154) */
+NS_GF inline double ns_ai_spline(double mui, double sig, double c, int n_ai, double j1, double j2, double dg0,
+                                 ns_fit_counters &cnt)
+{
+    const double sqrtV = sqrt(mui * (sig * mui + 1));
+    const double invsig = 1 / sig;
+    const double lg = log(mui / invsig + 1);
+    const double csd = c * sqrtV, mpi = mui + invsig;
+    ns_spline s;
+    ns_spline_init(s, n_ai, j1, j2);
+    if (s.by <= NS_STEP_BY) {
+        /* walk the lattice once by recurrence and sample it at the knots */
+        double pm = ns_dnbinom_mu(j1, invsig, mui);
+        double D = (j1 == 0) ? 0.0 : ns_digamma(j1 + invsig) - dg0;
+        const double q = mui / (mui + invsig);
+        int k = 0;
+        for (double j = j1;; j += 1) {
+            if (j == s.x[k]) {
+                double t = (j - mui) / csd;
+                double w = (t * t - 1) * (t * t - 1);
+                s.y[k] = w * (D - lg - (j - mui) / mpi) * pm;
+                if (++k == n_ai)
+                    break;
+            }
+            double ja = j + invsig, jb = j + 1;
+            double rr = 1.0 / (ja * jb);
+            pm *= (ja * ja) * rr * q;
+            D += jb * rr;
+        }
+    } else {
+        for (int k = 0; k < n_ai; k++) {
+            double j = s.x[k];
+            double t = (j - mui) / csd;
+            double w = (t * t - 1) * (t * t - 1);
+            double psi = ns_digamma(j + invsig) - dg0 - lg - (j - mui) / mpi;
+            s.y[k] = w * psi * ns_dnbinom_mu(j, invsig, mui);
+        }
+    }
+    ns_spline_diag(s);
+    ns_spline_solve(s);
+    int ier = 0, np = 0;
+    double v = ns_integrate_spline(s, ier, np);
+    cnt.n_quad += (unsigned long long)np;
+    if (ier == 7)
+        cnt.quad_overflow = 1;
+    if (ier != 0 || !(fabs(v) <= NS_DBL_MAX))
+        cnt.quad_err = 1;
+    return v;
+}
+
+/* ai.sig.tukey(mui, sig, c) (glm_rob_nb.r:141-160) */
+NS_GF inline double ns_ai_sig_tukey(double mui, double sig, double c, int n_ai, double dg0, ns_fit_counters &cnt)
+{
+    const double sqrtV = sqrt(mui * (sig * mui + 1));
+    const double j1 = fmax(ceil(mui - c * sqrtV), 0.0);
+    const double j2 = floor(mui + c * sqrtV);
+    cnt.n_seed += 1;
+    if (j1 > j2)
+        return 0.0;
+    if (j2 - j1 + 1 > 2 * n_ai) {
+        cnt.n_lattice += (unsigned long long)n_ai;
+        return ns_ai_spline(mui, sig, c, n_ai, j1, j2, dg0, cnt);
+    }
+    cnt.n_lattice += (unsigned long long)(j2 - j1 + 1);
+    return ns_ai_sum(mui, sig, c, j1, j2, dg0);
+}
+
+/* lattice-sum branch of E.tukeypsi.1 / .2 (glm_rob_nb.r:119-122, 135-138), both in one pass */
+NS_GF inline void ns_E12_sum(double mui, double sig, double c, double j1, double j2, double &e1, double &e2)
+{
+    const double sqrtV = sqrt(ns_varfunc(mui, sig));
+    const double size = 1 / sig, csd = c * sqrtV;
+    double pm = ns_dnbinom_mu(j1, size, mui);
+    const double q = mui / (mui + size);
+    double a1 = 0, a2 = 0;
+    for (double j = j1; j <= j2; j += 1) {
+        double d = j - mui;
+        double t = d / csd;
+        double w = (t * t - 1) * (t * t - 1);
+        double wp = w * pm;
+        a1 += wp * d;
+        a2 += wp * (d * d);
+        pm *= ((j + size) / (j + 1)) * q;
+    }
+    e1 = a1 / sqrtV;
+    e2 = a2 / sqrtV;
+}
+
+NS_GF inline void ns_E12_spline(double mui, double sig, double c, int n_ai, double j1, double j2,
+                                ns_fit_counters &cnt, double &e1, double &e2)
+{
+    const double sqrtV = sqrt(ns_varfunc(mui, sig));
+    const double size = 1 / sig, csd = c * sqrtV;
+    ns_spline s;
+    ns_spline_init(s, n_ai, j1, j2);
+    if (s.by <= NS_STEP_BY) {
+        double pm = ns_dnbinom_mu(j1, size, mui);
+        const double q = mui / (mui + size);
+        int k = 0;
+        for (double j = j1;; j += 1) {
+            if (j == s.x[k]) {
+                double t = (j - mui) / csd;
+                double w = (t * t - 1) * (t * t - 1);
+                s.y[k] = w * (j - mui) * pm;
+                if (++k == n_ai)
+                    break;
+            }
+            pm *= ((j + size) / (j + 1)) * q;
+        }
+    } else {
+        for (int k = 0; k < n_ai; k++) {
+            double j = s.x[k];
+            double t = (j - mui) / csd;
+            double w = (t * t - 1) * (t * t - 1);
+            s.y[k] = w * (j - mui) * ns_dnbinom_mu(j, size, mui);
+        }
+    }
+    ns_spline_diag(s);
+    ns_spline_solve(s);
+    int ier1 = 0, ier2 = 0, np = 0;
+    double v1 = ns_integrate_spline(s, ier1, np);
+    for (int k = 0; k < n_ai; k++)
+        s.y[k] *= (ns_knot(s, k) - mui); /* w*(j-mu)^2*pmf */
+    ns_spline_solve(s);
+    double v2 = ns_integrate_spline(s, ier2, np);
+    cnt.n_quad += (unsigned long long)np;
+    if (ier1 == 7 || ier2 == 7)
+        cnt.quad_overflow = 1;
+    if (ier1 != 0 || ier2 != 0 || !(fabs(v1) <= NS_DBL_MAX) || !(fabs(v2) <= NS_DBL_MAX))
+        cnt.quad_err = 1;
+    e1 = v1 / sqrtV;
+    e2 = v2 / sqrtV;
+}
+
+/* E.tukeypsi.1 and E.tukeypsi.2 (glm_rob_nb.r:109-140) */
+NS_GF inline void ns_E_tukeypsi_12(double mui, double sig, double c, int n_ai, ns_fit_counters &cnt, double &e1,
+                                   double &e2)
+{
+    const double sqrtV = sqrt(ns_varfunc(mui, sig));
+    const double j1 = fmax(ceil(mui - c * sqrtV), 0.0);
+    const double j2 = floor(mui + c * sqrtV);
+    cnt.n_seed += 1;
+    if (j1 > j2) {
+        e1 = 0;
+        e2 = 0;
+        return;
+    }
+    if (j2 - j1 + 1 > 2 * n_ai) {
+        cnt.n_lattice += (unsigned long long)n_ai;
+        ns_E12_spline(mui, sig, c, n_ai, j1, j2, cnt, e1, e2);
+        return;
+    }
+    cnt.n_lattice += (unsigned long long)(j2 - j1 + 1);
+    ns_E12_sum(mui, sig, c, j1, j2, e1, e2);
+}
+
+#if defined(__CUDACC__)
+/* out-of-line copies for the rare medium-length windows of the fast kernel */
+static __host__ __device__ __noinline__ double ns_ai_sum_ool(double mui, double sig, double c, double j1, double j2, double dg0)
+{
+    return ns_ai_sum(mui, sig, c, j1, j2, dg0);
+}
+static __host__ __device__ __noinline__ void ns_E12_sum_ool(double mui, double sig, double c, double j1, double j2, double *e1,
+                                            double *e2)
+{
+    ns_E12_sum(mui, sig, c, j1, j2, *e1, *e2);
+}
+static __host__ __device__ __noinline__ double ns_digamma_ool(double x) { return ns_digamma(x); }
+#define NS_AI_SUM_OOL ns_ai_sum_ool
+#define NS_E12_SUM_OOL(mu, sig, c, j1, j2, e1, e2) ns_E12_sum_ool(mu, sig, c, j1, j2, &(e1), &(e2))
+#define NS_DIGAMMA_OOL ns_digamma_ool
+#else
+#define NS_AI_SUM_OOL ns_ai_sum
+#define NS_E12_SUM_OOL(mu, sig, c, j1, j2, e1, e2) ns_E12_sum(mu, sig, c, j1, j2, e1, e2)
+#define NS_DIGAMMA_OOL ns_digamma
+#endif
+
+/* warp-cooperative versions for the heavy kernel (ns_coop.cuh, device only) */
+struct ns_coop_scratch {
+    double *y, *c, *ib, *m; /* NS_MAX_KNOTS each, per warp, shared memory */
+    const double *rt;       /* 1/j, j < rtn (CTA-shared) */
+    int rtn;
+};
+#if defined(__CUDACC__)
+static __device__ __noinline__ double ns_ai_coop(double mui, double sig, double c, int n_ai, double dg0,
+                                                 const ns_coop_scratch &sc, ns_fit_counters &cnt);
+static __device__ __noinline__ void ns_E12_coop(double mui, double sig, double c, int n_ai, const ns_coop_scratch &sc,
+                                                ns_fit_counters &cnt, double *e1, double *e2);
+#endif
+
+/* ---- per-group working set (slices of shared memory) ----------------------------- */
+struct ns_work {
+    double *y, *x, *X, *mu, *eta; /* n each; x <= 0 marks a sample that is not in the fit */
+    double *scratch;              /* n + 8 */
+    double *dtab;                 /* NS_JTAB: digamma(j+1/sig) - digamma(1/sig) for the current sigma */
+    const double *rtab;           /* NS_RTAB: 1/j (shared by the CTA) */
+    ns_coop_scratch coop;         /* MODE 2 only: this warp's spline arrays */
+};
+NS_HD size_t ns_work_doubles(int n) { return (size_t)6 * (size_t)n + 8 + NS_JTAB; }
+NS_HD void ns_work_bind(ns_work &w, double *base, int n, const double *rtab)
+{
+    w.y = base;
+    w.x = base + n;
+    w.X = base + 2 * (size_t)n;
+    w.mu = base + 3 * (size_t)n;
+    w.eta = base + 4 * (size_t)n;
+    w.scratch = base + 5 * (size_t)n;
+    w.dtab = base + 6 * (size_t)n + 8;
+    w.rtab = rtab;
+}
+
+struct ns_fit_result {
+    double sigma, slope;
+    uint32_t flags; /* NS_F_SIG_AT_MIN | NS_F_MAXIT | NS_F_QUAD_ERROR | NS_F_NAN_ROWS | NS_F_QUAD_OVERFLOW */
+    int n_outer, n_irls, n_obj;
+    int deferred; /* FAST only: the unit needs the spline branch, nothing else is valid */
+    ns_fit_counters cnt;
+};
+
+/* sig.rob.tukey(sig) (glm_rob_nb.r:161-165), summed over the group's samples */
+template <class G, int MODE>
+NS_GF inline double ns_sig_objective(double sig, const ns_work &w, int n, const ns_params &prm, ns_fit_counters &cnt,
+                                     int &need_heavy)
+{
+    const double c = prm.c_tukey_sig;
+    const double invsig = 1 / sig;
+    double acc = 0;
+    int qerr = 0;
+    if (MODE == 1) {
+        G::fill_dtab(w.dtab, invsig, NS_JTAB);
+        double dg0 = 0;
+        bool have_dg0 = false;
+        const double twon = (double)(2 * prm.n_ai_sig_tukey);
+        for (int i = G::lane(); i < n; i += G::nl()) {
+            if (!(w.x[i] > 0))
+                continue;
+            const double mu = w.mu[i], y = w.y[i];
+            const double s1 = sig * mu + 1;
+            const double sd = sqrt(mu * s1);
+            const double j1 = fmax(ceil(mu - c * sd), 0.0), j2 = floor(mu + c * sd);
+            cnt.n_seed += 1;
+            double term;
+            if (j1 == 0 && j2 < (double)NS_JTAB) {
+                /* window {0..j2}: everything by recurrence, no division inside the loop */
+                const double lg = log(s1);
+                double pm = exp(-invsig * lg); /* dnbinom(0) = (1+sig*mu)^(-1/sig) */
+                const double inv_csd = 1.0 / (c * sd), inv_mpi = 1.0 / (mu + invsig);
+                const double q = mu * inv_mpi;
+                const int J2 = (int)j2;
+                const int yi = (y <= j2) ? (int)y : -1;
+                double a = 0, ty = 0;
+                for (int j = 0; j <= J2; j++) {
+                    const double d = (double)j - mu;
+                    const double t = d * inv_csd;
+                    double wt = t * t - 1;
+                    wt *= wt;
+                    const double wpsi = wt * (w.dtab[j] - lg - d * inv_mpi);
+                    a += wpsi * pm;
+                    if (j == yi)
+                        ty = wpsi; /* (psi_c(r)/r) * psi.sig.ML(r) at r = (y-mu)/sd */
+                    pm *= ((double)j + invsig) * w.rtab[j + 1] * q;
+                }
+                term = ty - a;
+                if (y == mu)
+                    term = NAN; /* r == 0: tukeypsi(r)/r = 0/0 in R */
+                cnt.n_lattice += (unsigned long long)(J2 + 1);
+            } else if (j1 > j2) {
+                term = 0; /* cannot happen: kept for fidelity */
+                double r = (y - mu) / sd;
+                double wi = ns_tukeypsi(r, c) / r;
+                if (wi != 0.0)
+                    term = NAN;
+            } else if (j2 - j1 + 1 > twon) {
+                need_heavy = 1;
+                term = 0;
+            } else {
+                if (!have_dg0) {
+                    dg0 = NS_DIGAMMA_OOL(invsig);
+                    have_dg0 = true;
+                }
+                double r = (y - mu) / sqrt(ns_varfunc(mu, sig));
+                double wi = ns_tukeypsi(r, c) / r;
+                term = 0.0;
+                if (wi != 0.0) {
+                    double psiML = NS_DIGAMMA_OOL(r * sqrt(mu * (sig * mu + 1)) + mu + invsig) -
+                                   sig * r * sqrt(mu / (sig * mu + 1)) - dg0 - log(sig * mu + 1);
+                    term = wi * psiML;
+                }
+                term -= NS_AI_SUM_OOL(mu, sig, c, j1, j2, dg0);
+                cnt.n_lattice += (unsigned long long)(j2 - j1 + 1);
+            }
+            acc += term;
+        }
+    } else {
+        const double dg0 = ns_digamma(invsig);
+        for (int i = G::lane(); i < n; i += G::nl()) {
+            if (!(w.x[i] > 0))
+                continue;
+            double mu = w.mu[i], y = w.y[i];
+            double sd = sqrt(ns_varfunc(mu, sig));
+            double r = (y - mu) / sd;
+            double wi = ns_tukeypsi(r, c) / r; /* r == 0 -> NaN, as in R */
+            double term;
+            if (wi == 0.0) {
+                term = 0.0; /* 0 * finite psi.sig.ML */
+            } else {
+                double psiML = ns_digamma(r * sqrt(mu * (sig * mu + 1)) + mu + 1 / sig) -
+                               sig * r * sqrt(mu / (sig * mu + 1)) - dg0 - log(sig * mu + 1);
+                term = wi * psiML;
+            }
+            int qe0 = cnt.quad_err;
+            cnt.quad_err = 0;
+#if defined(__CUDA_ARCH__)
+            if (MODE == 2)
+                term -= ns_ai_coop(mu, sig, c, prm.n_ai_sig_tukey, dg0, w.coop, cnt);
+            else
+#endif
+                term -= ns_ai_sig_tukey(mu, sig, c, prm.n_ai_sig_tukey, dg0, cnt);
+            qerr |= cnt.quad_err;
+            cnt.quad_err = qe0;
+            acc += term;
+        }
+    }
+    acc = G::sum(acc);
+    if (G::any(qerr))
+        return NAN; /* integrate() error inside uniroot -> tryCatch -> NA (:175-177) */
+    return acc;
+}
+
+/* uniroot(sig.rob.tukey, c(minsig,maxsig), tol=sig.prec, maxiter=maxit.sig)$root: R's
+ * end-point checks followed by R_zeroin2 (Brent).  Returns false on any R error. */
+template <class G, int MODE>
+NS_GF inline bool ns_sigma_root(const ns_work &w, int n, const ns_params &prm, ns_fit_result &res, double &root,
+                                int &need_heavy)
+{
+    double a = prm.minsig, b = prm.maxsig;
+    double fa = ns_sig_objective<G, MODE>(a, w, n, prm, res.cnt, need_heavy);
+    double fb = ns_sig_objective<G, MODE>(b, w, n, prm, res.cnt, need_heavy);
+    res.n_obj += 2;
+    if (MODE == 1 && G::any(need_heavy))
+        return false;
+    if (fa != fa || fb != fb)
+        return false;
+    if (fa * fb > 0)
+        return false;
+    double c = a, fc = fa;
+    if (fa == 0.0) {
+        root = a;
+        return true;
+    }
+    if (fb == 0.0) {
+        root = b;
+        return true;
+    }
+    int maxit = prm.maxit_sig + 1;
+    const double tol = prm.sig_prec;
+    while (maxit--) {
+        double prev_step = b - a;
+        if (fabs(fc) < fabs(fb)) {
+            a = b;
+            b = c;
+            c = a;
+            fa = fb;
+            fb = fc;
+            fc = fa;
+        }
+        double tol_act = 2 * NS_DBL_EPS * fabs(b) + tol / 2;
+        double new_step = (c - b) / 2;
+        if (fabs(new_step) <= tol_act || fb == 0.0) {
+            root = b;
+            return true;
+        }
+        if (fabs(prev_step) >= tol_act && fabs(fa) > fabs(fb)) {
+            double p, q, cb = c - b;
+            if (a == c) {
+                double t1 = fb / fa;
+                p = cb * t1;
+                q = 1.0 - t1;
+            } else {
+                double t1, t2;
+                q = fa / fc;
+                t1 = fb / fc;
+                t2 = fb / fa;
+                p = t2 * (cb * q * (q - t1) - (b - a) * (t1 - 1.0));
+                q = (q - 1.0) * (t1 - 1.0) * (t2 - 1.0);
+            }
+            if (p > 0.0)
+                q = -q;
+            else
+                p = -p;
+            if (p < (0.75 * cb * q - fabs(tol_act * q) / 2) && p < fabs(prev_step * q / 2))
+                new_step = p / q;
+        }
+        if (fabs(new_step) < tol_act)
+            new_step = (new_step > 0.0) ? tol_act : -tol_act;
+        a = b;
+        fa = fb;
+        b += new_step;
+        fb = ns_sig_objective<G, MODE>(b, w, n, prm, res.cnt, need_heavy);
+        res.n_obj += 1;
+        if (MODE == 1 && G::any(need_heavy))
+            return false;
+        if (fb != fb || fb == INFINITY)
+            return false; /* "invalid function value in 'zeroin'" */
+        if (fb == -INFINITY)
+            fb = -NS_DBL_MAX;
+        if ((fb > 0 && fc > 0) || (fb < 0 && fc < 0)) {
+            c = a;
+            fc = fa;
+        }
+    }
+    root = b; /* maxiter reached: a warning in R, the current b is returned */
+    return true;
+}
+
+/* abs(max(u - v)) with R's recycling, for u, v of length 1 or 2 (second entry of a
+ * length-2 vector is the constant 1 of c(coef(wls), 1); glm_rob_nb.r:171,187,195) */
+NS_HD double ns_D_absmax(double u0, int ulen, double v0, int vlen)
+{
+    double d0 = u0 - v0;
+    double d1 = (ulen == 2 ? 1.0 : u0) - (vlen == 2 ? 1.0 : v0);
+    if (ulen == 1 && vlen == 1)
+        return fabs(d0);
+    if (d0 != d0 || d1 != d1)
+        return NAN;
+    return fabs(fmax(d0, d1));
+}
+
+/* one IRLS pass (glm_rob_nb.r:188-200): returns the new beta, updates mu/eta */
+template <class G, int MODE>
+NS_GF inline double ns_irls_step(double sig, const ns_work &w, int n, double maxmu, const ns_params &prm,
+                                 ns_fit_result &res, int &need_heavy)
+{
+    const int lane = G::lane();
+    const double c = prm.c_tukey_beta;
+    const double invsig = 1 / sig;
+    const double twon = (double)(2 * prm.n_ai_sig_tukey);
+    double sw = 0, swz = 0;
+    int nanrows = 0;
+    for (int i = lane; i < n; i += G::nl()) {
+        if (!(w.x[i] > 0))
+            continue;
+        const double mu = w.mu[i], eta = w.eta[i], y = w.y[i];
+        double e1, sap;
+        const double V = ns_varfunc(mu, sig);
+        const double sV = sqrt(V);
+        if (MODE == 1) {
+            const double j1 = fmax(ceil(mu - c * sV), 0.0), j2 = floor(mu + c * sV);
+            res.cnt.n_seed += 1;
+            if (j1 == 0 && j2 < (double)(NS_RTAB - 1)) {
+                double pm = exp(-invsig * log(sig * mu + 1));
+                const double inv_csd = 1.0 / (c * sV);
+                const double q = mu / (mu + invsig);
+                const int J2 = (int)j2;
+                double a1 = 0, a2 = 0;
+                for (int j = 0; j <= J2; j++) {
+                    const double d = (double)j - mu;
+                    const double t = d * inv_csd;
+                    double wt = t * t - 1;
+                    wt *= wt;
+                    const double wp = wt * pm;
+                    a1 += wp * d;
+                    a2 += wp * (d * d);
+                    pm *= ((double)j + invsig) * w.rtab[j + 1] * q;
+                }
+                e1 = a1 / sV;
+                sap = a2 / sV;
+                res.cnt.n_lattice += (unsigned long long)(J2 + 1);
+            } else if (j1 > j2) {
+                e1 = 0;
+                sap = 0;
+            } else if (j2 - j1 + 1 > twon) {
+                need_heavy = 1;
+                continue;
+            } else {
+                NS_E12_SUM_OOL(mu, sig, c, j1, j2, e1, sap);
+                res.cnt.n_lattice += (unsigned long long)(j2 - j1 + 1);
+            }
+        } else {
+#if defined(__CUDA_ARCH__)
+            if (MODE == 2)
+                ns_E12_coop(mu, sig, c, prm.n_ai_sig_tukey, w.coop, res.cnt, &e1, &sap);
+            else
+#endif
+                ns_E_tukeypsi_12(mu, sig, c, prm.n_ai_sig_tukey, res.cnt, e1, sap);
+        }
+        double ee = (MODE == 1) ? mu : exp(eta); /* derivinvlink(eta) = exp(log(mu)) */
+        double bi = sap * (1.0 / (V * sV)) * (ee * ee);
+        double ei = (ns_tukeypsi((y - mu) / sV, c) - e1) / sap * V * (1 / mu);
+        double zi = eta + ei;
+        if (bi != bi || zi != zi) {
+            nanrows++; /* lm(): na.omit drops the row */
+            continue;
+        }
+        if (bi == 0)
+            continue; /* lm.wfit(): zero-weight rows excluded */
+        sw += bi;
+        swz += bi * (zi - w.X[i]);
+    }
+    sw = G::sum(sw);
+    swz = G::sum(swz);
+    if (G::any(nanrows))
+        res.flags |= NS_F_NAN_ROWS;
+    const double beta = swz / sw;
+    G::sync();
+    for (int i = lane; i < n; i += G::nl()) {
+        if (!(w.x[i] > 0))
+            continue;
+        double mu = exp(w.X[i] + beta);
+        if (mu > maxmu)
+            mu = maxmu;
+        if (mu == 0)
+            mu = prm.minmu;
+        w.mu[i] = mu;
+        w.eta[i] = log(mu);
+    }
+    G::sync();
+    return beta;
+}
+
+/* The fit proper: glm_rob_nb.r:58-205 on the samples with w.x[i] > 0.
+ * Expects w.y / w.x filled (x <= 0 for samples outside the fit); maxmu = max(x) over ALL
+ * samples of the unit (:20). */
+template <class G, int MODE>
+NS_GF inline void ns_fit_unit(const ns_work &w, int n, double maxmu, const ns_params &prm, ns_fit_result &res)
+{
+    const int lane = G::lane();
+    res.flags = 0;
+    res.n_outer = res.n_irls = res.n_obj = 0;
+    res.deferred = 0;
+    res.sigma = res.slope = NAN;
+    res.cnt.n_seed = res.cnt.n_lattice = res.cnt.n_quad = 0;
+    res.cnt.quad_err = res.cnt.quad_overflow = 0;
+    /* :58-63, :75-76 */
+    int nfit = 0;
+    double sum_ex = 0;
+    for (int i = lane; i < n; i += G::nl()) {
+        double x = w.x[i];
+        if (x > 0) {
+            double X = log(x);
+            w.X[i] = X;
+            double ex = exp(X);
+            double y = w.y[i];
+            w.eta[i] = (y == 0) ? 0.0 : y / ex; /* af, parked in eta until mu is known */
+            sum_ex += ex;
+            nfit++;
+        }
+    }
+    nfit = G::isum(nfit);
+    sum_ex = G::sum(sum_ex);
+    G::sync();
+    /* :77 type-7 quartiles of af by rank counting */
+    const double h25 = (double)(nfit - 1) * 0.25, h75 = (double)(nfit - 1) * 0.75;
+    const int lo25 = (int)floor(h25), hi25 = (int)ceil(h25), lo75 = (int)floor(h75), hi75 = (int)ceil(h75);
+    double v0 = 0, v1 = 0, v2 = 0, v3 = 0;
+    for (int i = lane; i < n; i += G::nl()) {
+        if (!(w.x[i] > 0))
+            continue;
+        double ai = w.eta[i];
+        int rank = 0;
+        for (int j = 0; j < n; j++) {
+            double aj = w.eta[j];
+            rank += (w.x[j] > 0) && (aj < ai || (aj == ai && j < i));
+        }
+        if (rank == lo25)
+            v0 = ai;
+        if (rank == hi25)
+            v1 = ai;
+        if (rank == lo75)
+            v2 = ai;
+        if (rank == hi75)
+            v3 = ai;
+    }
+    v0 = G::sum(v0);
+    v1 = G::sum(v1);
+    v2 = G::sum(v2);
+    v3 = G::sum(v3);
+    double q25 = v0, q75 = v2;
+    if (h25 > (double)lo25 && v1 != v0) {
+        double h = h25 - (double)lo25;
+        q25 = (1 - h) * v0 + h * v1;
+    }
+    if (h75 > (double)lo75 && v3 != v2) {
+        double h = h75 - (double)lo75;
+        q75 = (1 - h) * v2 + h * v3;
+    }
+    const double fence = q75 + 1.5 * (q75 - q25);
+    double s_af = 0;
+    int c_af = 0;
+    for (int i = lane; i < n; i += G::nl())
+        if (w.x[i] > 0 && w.eta[i] <= fence) {
+            s_af += w.eta[i];
+            c_af++;
+        }
+    s_af = G::sum(s_af);
+    c_af = G::isum(c_af);
+    double inislope = s_af / (double)c_af;
+    {
+        double mean_ex = sum_ex / (double)nfit;
+        if (inislope <= 1 / (10 * mean_ex))
+            inislope = 1 / (10 * mean_ex); /* :78 */
+    }
+    G::sync();
+    /* :79-86 */
+    double s_sig = 0;
+    for (int i = lane; i < n; i += G::nl()) {
+        if (!(w.x[i] > 0))
+            continue;
+        double mu = inislope * exp(w.X[i]);
+        if (mu > maxmu)
+            mu = maxmu;
+        if (mu < prm.minmu)
+            mu = prm.minmu;
+        w.mu[i] = mu;
+        w.eta[i] = log(mu);
+        double t = w.y[i] / mu - 1;
+        s_sig += t * t;
+    }
+    s_sig = G::sum(s_sig);
+    double sig = s_sig / (double)nfit;
+    if (sig > prm.maxsig)
+        sig = prm.maxsig;
+    if (sig < prm.minsig)
+        sig = prm.minsig;
+    G::sync();
+
+    /* :166-205 alternation */
+    const double tol = prm.tol;
+    double sig0 = sig + 1 + tol;
+    double beta11 = log(inislope);
+    int len11 = 1;
+    double beta00 = beta11 + tol + 1;
+    int len00 = 1;
+    double beta1 = beta11;
+    int len1 = 1;
+    int it = 0;
+    int last_sig_failed = 0;
+    int need_heavy = 0;
+    while ((fabs(sig - sig0) > tol || ns_D_absmax(beta11, len11, beta00, len00) > tol) && it < prm.maxit) {
+        sig0 = sig;
+        beta00 = beta11;
+        len00 = len11;
+        /* :175-182 */
+        double root = NAN;
+        bool ok = ns_sigma_root<G, MODE>(w, n, prm, res, root, need_heavy);
+        if (MODE == 1 && G::any(need_heavy)) {
+            res.deferred = 1;
+            return;
+        }
+        if (!ok || root != root) {
+            sig = prm.minsig;
+            last_sig_failed = 1;
+        } else {
+            sig = root;
+            last_sig_failed = 0;
+            if (sig > prm.maxsig)
+                sig = prm.maxsig;
+            if (sig < prm.minsig)
+                sig = prm.minsig;
+        }
+        /* :184-202 */
+        beta1 = log(inislope);
+        len1 = 1;
+        double beta0 = beta1 + tol + 1;
+        int len0 = 1;
+        int it_mu = 0;
+        while (ns_D_absmax(beta1, len1, beta0, len0) > tol && it_mu < prm.maxit) {
+            beta0 = beta1;
+            len0 = len1;
+            beta1 = ns_irls_step<G, MODE>(sig, w, n, maxmu, prm, res, need_heavy);
+            len1 = 2;
+            if (MODE == 1 && G::any(need_heavy)) {
+                res.deferred = 1;
+                return;
+            }
+            it_mu++;
+            res.n_irls++;
+        }
+        if (G::any(res.cnt.quad_err))
+            res.flags |= NS_F_QUAD_ERROR; /* R would have stopped the script */
+        res.cnt.quad_err = 0;
+        beta11 = beta1;
+        len11 = len1;
+        it++;
+    }
+    if (G::any(res.cnt.quad_overflow))
+        res.flags |= NS_F_QUAD_OVERFLOW;
+    res.n_outer = it;
+    if (it >= prm.maxit)
+        res.flags |= NS_F_MAXIT;
+    if (last_sig_failed)
+        res.flags |= NS_F_SIG_AT_MIN;
+    double slope = exp(beta1);
+    if (slope > 1)
+        slope = 1;
+    res.sigma = sig;
+    res.slope = slope;
+}

@@ -1,0 +1,60 @@
+/* ns_k_post.cu — p/q/GQ, Holm power q-values, T/N status, strand bias, genotypes; y* tables (sm_100a) */
+#include "ns_kernels.cuh"
+
+extern __shared__ double ns_smem[];
+
+__global__ void k_post(ns_unit_src src, ns_params prm, int64_t u0, ns_unit_arrays ua, ns_planes pl,
+                       const double *qtab, int qtab_len, ns_counters *cnt)
+{
+    const int n = src.n;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    double *sm = ns_smem + (size_t)warp * (3 * (size_t)n + 8);
+    const int n_post = cnt->n_post;
+    for (;;) {
+        int idx = 0;
+        if (lane == 0)
+            idx = atomicAdd(&cnt->next_post, 1);
+        idx = __shfl_sync(0xffffffffu, idx, 0);
+        if (idx >= n_post)
+            break;
+        const int u = ua.post_list[idx];
+        const size_t row = (size_t)ua.row[u];
+        ns_rows r = ns_unit_rows(src, u0 + u);
+        ns_unit_out o;
+        o.pvalue = pl.pvalue + row * n;
+        o.qvalue = pl.qvalue + row * n;
+        o.gq = pl.gq + row * n;
+        o.qval_minaf = pl.qval_minaf + row * n;
+        o.sor = pl.sor + row * n;
+        o.rvsb = pl.rvsb + row * n;
+        o.fs = pl.fs + row * n;
+        o.gt = pl.gt + row * n;
+        o.status = pl.status + row * n;
+        o.pooled = pl.pooled + row * 8;
+        if (lane < 8)
+            o.pooled[lane] = NAN;
+        double mg = 0;
+        uint32_t flags = ns_post_unit<WarpG>(r, n, prm, ua.flags[u], ua.sigma[u], ua.slope[u], qtab, qtab_len,
+                                             o, sm, mg);
+        if (lane == 0) {
+            ua.flags[u] = flags;
+            ua.max_gq[u] = mg;
+            bool emit = prm.emit_mode == NS_EMIT_ALL || (prm.emit_mode == NS_EMIT_FITTED && !(flags & NS_F_GATED)) ||
+                        (flags & NS_F_GATE2);
+            ua.emitflag[u] = emit;
+        }
+        __syncwarp();
+    }
+}
+
+/* y* tables of toQvalueN / toQvalueT (needlestack.r:243,249): they depend on the depth only */
+__global__ void k_qtab(double *tabN, double *tabT, int len, double sigma_normal, double afmin)
+{
+    int x = blockIdx.x * blockDim.x + threadIdx.x;
+    if (x >= len)
+        return;
+    tabN[x] = ns_qnbinom_mu(0.01, 1 / sigma_normal, 0.5 * (double)x);
+    if (tabT)
+        tabT[x] = (afmin >= 0) ? ns_qbinom(0.01, (double)x, afmin) : 0.0;
+}
+

@@ -1,0 +1,54 @@
+/*
+ * ns_kernels.cuh — device-side bookkeeping structs and kernel declarations shared by the
+ * translation units of libns_b200.so (kernels are split over several .cu files so that the
+ * in-tree build compiles them in parallel).
+ */
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "ns_core.cuh"
+
+#define NS_COOP_DOUBLES (4 * NS_MAX_KNOTS)
+#define NS_RTAB_HEAVY 4096
+#ifndef NS_HEAVY_THREADS
+#define NS_HEAVY_THREADS 512 /* 16 warps = 16 samples of one unit in flight */
+#endif
+
+#define NS_WPB_GATE 8
+#define NS_QTAB_LEN 65536
+
+/* ---- device-side bookkeeping ------------------------------------------------------- */
+struct ns_counters {
+    int n_fit, n_post, n_rows, n_emit;
+    int next_fit, next_post, n_heavy, next_heavy;
+    int n_pre, next_pre, n_light, pad1; /* n_pre: units predicted heavy by the gate kernel; n_light: the rest */
+    unsigned long long n_seed, n_lattice, n_quad, pad2;
+    unsigned long long fast_seed, fast_lattice;
+};
+
+struct ns_planes {
+    double *pvalue, *qvalue, *gq, *qval_minaf, *sor, *rvsb, *fs, *pooled;
+    uint8_t *gt, *status;
+};
+
+struct ns_unit_arrays {
+    uint32_t *flags, *iters;
+    unsigned long long *cycles;
+    double *sigma, *slope, *max_gq;
+    int *needrow, *row, *emitflag, *emitidx;
+    int *fit_list, *post_list, *heavy_list, *pre_list;
+};
+
+
+__global__ void k_gate(ns_unit_src src, ns_params prm, int64_t u0, int n_units, ns_unit_arrays ua, ns_counters *cnt);
+__global__ void k_fit(ns_unit_src src, ns_params prm, int64_t u0, ns_unit_arrays ua, ns_counters *cnt);
+__global__ void k_fit_heavy(ns_unit_src src, ns_params prm, int64_t u0, ns_unit_arrays ua, ns_counters *cnt,
+                            int which);
+__global__ void k_post(ns_unit_src src, ns_params prm, int64_t u0, ns_unit_arrays ua, ns_planes pl,
+                       const double *qtab, int qtab_len, ns_counters *cnt);
+__global__ void k_scan_total(const int *flag, const int *excl, int n, int *total);
+__global__ void k_pack(int n, int n_units, int64_t u0, int64_t emit_off, int cap, ns_unit_arrays ua,
+                       ns_planes src, ns_planes dst, int64_t *emit_unit, int *emit_index_out);
+__global__ void k_qtab(double *tabN, double *tabT, int len, double sigma_normal, double afmin);
+__global__ void k_dfma(double *out, int iters, double a, double b);

@@ -62,12 +62,16 @@
      0.219086362515982043995534934228163, 0.269266719309996355091226921569469,                     \
      0.295524224714752870173892994651338}
 
+#define NS_ODDRCP_INIT {1.0 / 1.0, 1.0 / 3.0, 1.0 / 5.0, 1.0 / 7.0, 1.0 / 9.0, 1.0 / 11.0, 1.0 / 13.0, 1.0 / 15.0, 1.0 / 17.0, 1.0 / 19.0, 1.0 / 21.0, 1.0 / 23.0, 1.0 / 25.0, 1.0 / 27.0, 1.0 / 29.0, 1.0 / 31.0, 1.0 / 33.0, 1.0 / 35.0, 1.0 / 37.0, 1.0 / 39.0, 1.0 / 41.0, 1.0 / 43.0, 1.0 / 45.0, 1.0 / 47.0, 1.0 / 49.0, 1.0 / 51.0, 1.0 / 53.0, 1.0 / 55.0, 1.0 / 57.0, 1.0 / 59.0, 1.0 / 61.0, 1.0 / 63.0, 1.0 / 65.0, 1.0 / 67.0, 1.0 / 69.0, 1.0 / 71.0, 1.0 / 73.0, 1.0 / 75.0, 1.0 / 77.0, 1.0 / 79.0, 1.0 / 81.0, 1.0 / 83.0, 1.0 / 85.0, 1.0 / 87.0, 1.0 / 89.0, 1.0 / 91.0, 1.0 / 93.0, 1.0 / 95.0, 1.0 / 97.0, 1.0 / 99.0, 1.0 / 101.0, 1.0 / 103.0, 1.0 / 105.0, 1.0 / 107.0, 1.0 / 109.0, 1.0 / 111.0, 1.0 / 113.0, 1.0 / 115.0, 1.0 / 117.0, 1.0 / 119.0, 1.0 / 121.0, 1.0 / 123.0, 1.0 / 125.0, 1.0 / 127.0}
+
 #if defined(__CUDACC__)
-__constant__ double ns_d_sferr[31] = NS_SFERR_INIT;
-__constant__ double ns_d_xgk[11] = NS_XGK_INIT;
-__constant__ double ns_d_wgk[11] = NS_WGK_INIT;
-__constant__ double ns_d_wg[5] = NS_WG_INIT;
+static __constant__ double ns_d_oddrcp[64] = NS_ODDRCP_INIT;
+static __constant__ double ns_d_sferr[31] = NS_SFERR_INIT;
+static __constant__ double ns_d_xgk[11] = NS_XGK_INIT;
+static __constant__ double ns_d_wgk[11] = NS_WGK_INIT;
+static __constant__ double ns_d_wg[5] = NS_WG_INIT;
 #endif
+static const double ns_h_oddrcp[64] = NS_ODDRCP_INIT;
 static const double ns_h_sferr[31] = NS_SFERR_INIT;
 static const double ns_h_xgk[11] = NS_XGK_INIT;
 static const double ns_h_wgk[11] = NS_WGK_INIT;
@@ -113,7 +117,8 @@ NS_HD double ns_bd0(double x, double np)
         v = v * v;
         for (int j = 1; j < 1000; j++) {
             ej *= v;
-            double s1 = s + ej / (double)((j << 1) + 1);
+            /* R divides by 2j+1; the correctly rounded reciprocal differs by at most one ulp per term */
+            double s1 = s + (j < 64 ? ej * NS_TBL(oddrcp)[j] : ej / (double)((j << 1) + 1));
             if (s1 == s)
                 return s1;
             s = s1;
@@ -170,9 +175,11 @@ NS_HD double ns_dnbinom_mu(double x, double size, double mu)
  * x >= 12 then the asymptotic series; glm_rob_nb.r:102,143 */
 NS_HD double ns_digamma(double x)
 {
-    double acc = 0.0;
+    /* sum_{k<m} 1/(x+k) as one fraction num/den (m <= 12 terms, den <= 12^12): one division */
+    double num = 0.0, den = 1.0;
     while (x < 12.0) {
-        acc -= 1.0 / x;
+        num = num * x + den;
+        den *= x;
         x += 1.0;
     }
     double r = 1.0 / x, r2 = r * r;
@@ -182,7 +189,8 @@ NS_HD double ns_digamma(double x)
                                  r2 * (1.0 / 240 -
                                        r2 * (1.0 / 132 -
                                              r2 * (691.0 / 32760 - r2 * (1.0 / 12)))))));
-    return acc + log(x) - 0.5 * r - s;
+    double head = log(x) - 0.5 * r - s;
+    return (num == 0.0) ? head : head - num / den;
 }
 
 /* ---------------------------------------------------------------------------------

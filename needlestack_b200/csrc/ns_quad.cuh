@@ -18,25 +18,18 @@
 #define NS_MAX_KNOTS 128 /* n_ai.sig.tukey <= 128 (reference default 100) */
 #define NS_QLIMIT 24     /* on-chip subdivision list; R's limit is 100 */
 
-/* The spline through (t_k, y_k), k = 0..n-1, t_k = round(j1 + k*by) (glm_rob_nb.r:116).
- * Knots are recomputed from (j1, by); y and the second-derivative array c are stored. */
+/* The spline through (t_k, y_k), k = 0..n-1, t_k = round(seq(j1, j2, length.out = n))
+ * (glm_rob_nb.r:116).  x, y and the second-derivative array c are stored per lane. */
 struct ns_spline {
     int n;
     double j1, j2, by;
+    double x[NS_MAX_KNOTS];
     double y[NS_MAX_KNOTS];
-    double c[NS_MAX_KNOTS]; /* R's c[] before the final 3x scaling */
+    double c[NS_MAX_KNOTS];  /* R's c[] before the final 3x scaling */
     double bm[NS_MAX_KNOTS]; /* eliminated diagonal (depends on the knots only) */
 };
 
-NS_HD double ns_knot(const ns_spline &s, int k)
-{
-    /* seq(j1, j2, length.out = n): c(from, from + (1:(n-2))*by, to), then round() */
-    if (k <= 0)
-        return s.j1;
-    if (k >= s.n - 1)
-        return s.j2;
-    return nearbyint(s.j1 + (double)k * s.by);
-}
+NS_HD double ns_knot(const ns_spline &s, int k) { return s.x[k]; }
 
 NS_HD void ns_spline_init(ns_spline &s, int n, double j1, double j2)
 {
@@ -44,6 +37,11 @@ NS_HD void ns_spline_init(ns_spline &s, int n, double j1, double j2)
     s.j1 = j1;
     s.j2 = j2;
     s.by = (j2 - j1) / (double)(n - 1);
+    /* seq(j1, j2, length.out = n): c(from, from + (1:(n-2))*by, to), then round() */
+    s.x[0] = j1;
+    for (int k = 1; k < n - 1; k++)
+        s.x[k] = nearbyint(j1 + (double)k * s.by);
+    s.x[n - 1] = j2;
 }
 
 /* forward elimination of the diagonal: only the knot spacing enters (R splines.c
@@ -51,10 +49,10 @@ NS_HD void ns_spline_init(ns_spline &s, int n, double j1, double j2)
 NS_HD void ns_spline_diag(ns_spline &s)
 {
     const int n = s.n;
-    double dprev = ns_knot(s, 1) - ns_knot(s, 0); /* d[1] */
+    double dprev = s.x[1] - s.x[0]; /* d[1] */
     double bprev = 0;
     for (int i = 1; i <= n - 2; i++) {
-        double di = ns_knot(s, i + 1) - ns_knot(s, i);
+        double di = s.x[i + 1] - s.x[i];
         double bi = 2 * (dprev + di);
         if (i >= 2) {
             double t = dprev / bprev;
@@ -71,11 +69,11 @@ NS_HD void ns_spline_solve(ns_spline &s)
 {
     const int n = s.n;
     /* c[i] = (y[i+1]-y[i])/d[i] - (y[i]-y[i-1])/d[i-1] */
-    double dprev = ns_knot(s, 1) - ns_knot(s, 0);
+    double dprev = s.x[1] - s.x[0];
     double sprev = (s.y[1] - s.y[0]) / dprev;
     double cprev = 0;
     for (int i = 1; i <= n - 2; i++) {
-        double di = ns_knot(s, i + 1) - ns_knot(s, i);
+        double di = s.x[i + 1] - s.x[i];
         double snext = (s.y[i + 1] - s.y[i]) / di;
         double ci = snext - sprev;
         if (i >= 2) {
@@ -89,7 +87,7 @@ NS_HD void ns_spline_solve(ns_spline &s)
     }
     s.c[n - 2] = s.c[n - 2] / s.bm[n - 2];
     for (int i = n - 3; i >= 1; i--) {
-        double di = ns_knot(s, i + 1) - ns_knot(s, i);
+        double di = s.x[i + 1] - s.x[i];
         s.c[i] = (s.c[i] - di * s.c[i + 1]) / s.bm[i];
     }
     s.c[0] = 0.0;
@@ -106,24 +104,24 @@ NS_HD double ns_spline_eval(const ns_spline &s, double u)
         i = 0;
     if (i > n - 1)
         i = n - 1;
-    while (i > 0 && u < ns_knot(s, i))
+    while (i > 0 && u < s.x[i])
         i--;
-    while (i < n - 1 && u >= ns_knot(s, i + 1))
+    while (i < n - 1 && u >= s.x[i + 1])
         i++;
-    double xi = ns_knot(s, i);
+    double xi = s.x[i];
     double dx = u - xi;
     if (i == n - 1) {
-        double dl = xi - ns_knot(s, n - 2);
+        double dl = xi - s.x[n - 2];
         double bl = (s.y[n - 1] - s.y[n - 2]) / dl + dl * s.c[n - 2];
-        return s.y[i] + dx * (bl + dx * (0.0 + dx * 0.0));
+        return s.y[i] + dx * bl;
     }
-    double di = ns_knot(s, i + 1) - xi;
-    double b = (s.y[i + 1] - s.y[i]) / di - di * (s.c[i + 1] + 2.0 * s.c[i]);
-    double d = (s.c[i + 1] - s.c[i]) / di;
-    double c = 3.0 * s.c[i];
+    double di = s.x[i + 1] - xi;
+    double c0 = s.c[i], c1 = s.c[i + 1];
+    double b = (s.y[i + 1] - s.y[i]) / di - di * (c1 + 2.0 * c0);
+    double d = (c1 - c0) / di;
     if (u < s.j1)
         d = 0.0;
-    return s.y[i] + dx * (b + dx * (c + dx * d));
+    return s.y[i] + dx * (b + dx * (3.0 * c0 + dx * d));
 }
 
 /* ---- QUADPACK ------------------------------------------------------------------ */
@@ -319,8 +317,17 @@ NS_HD void ns_dqelg(int &n, double *epstab, double &result, double &abserr, doub
 
 /* dqagse with R's limit (100) semantics but an on-chip list of NS_QLIMIT intervals.
  * ier: 0 ok, 1..6 as QUADPACK (an R error), 7 = on-chip list exhausted. */
-template <class F>
-NS_HD void ns_dqagse(const F &f, double a, double b, double epsabs, double epsrel, ns_quad_out &out)
+struct ns_k21_serial {
+    template <class F>
+    static NS_HD void eval(const F &f, double a, double b, double &result, double &abserr, double &resabs,
+                           double &resasc)
+    {
+        ns_dqk21(f, a, b, result, abserr, resabs, resasc);
+    }
+};
+
+template <class K21, class F>
+NS_HD void ns_dqagse_t(const F &f, double a, double b, double epsabs, double epsrel, ns_quad_out &out)
 {
     const int limit = 100; /* R's integrate() default; decides jupbnd / ier=1 */
     double alist[NS_QLIMIT + 2], blist[NS_QLIMIT + 2], rlist[NS_QLIMIT + 2], elist[NS_QLIMIT + 2];
@@ -338,7 +345,7 @@ NS_HD void ns_dqagse(const F &f, double a, double b, double epsabs, double epsre
     rlist[1] = 0;
     elist[1] = 0;
     res3la[1] = res3la[2] = res3la[3] = 0;
-    ns_dqk21(f, a, b, result, abserr, defabs, resabs);
+    K21::eval(f, a, b, result, abserr, defabs, resabs);
     dres = fabs(result);
     errbnd = fmax(epsabs, epsrel * dres);
     last = 1;
@@ -376,8 +383,8 @@ NS_HD void ns_dqagse(const F &f, double a, double b, double epsabs, double epsre
         a2 = b1;
         b2 = blist[maxerr];
         erlast = errmax;
-        ns_dqk21(f, a1, b1, area1, error1, resabs, defab1);
-        ns_dqk21(f, a2, b2, area2, error2, resabs, defab2);
+        K21::eval(f, a1, b1, area1, error1, resabs, defab1);
+        K21::eval(f, a2, b2, area2, error2, resabs, defab2);
         area12 = area1 + area2;
         erro12 = error1 + error2;
         errsum = errsum + erro12 - errmax;
@@ -545,6 +552,12 @@ NS_HD void ns_dqagse(const F &f, double a, double b, double epsabs, double epsre
     out.neval = last * 42 - 21;
     out.ier = ier;
     out.last = last;
+}
+
+template <class F>
+NS_HD void ns_dqagse(const F &f, double a, double b, double epsabs, double epsrel, ns_quad_out &out)
+{
+    ns_dqagse_t<ns_k21_serial>(f, a, b, epsabs, epsrel, out);
 }
 
 struct ns_spline_fn {

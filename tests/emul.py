@@ -19,7 +19,7 @@ def build():
     src = os.path.join(_HERE, "emul", "ns_emul.cpp")
     out = os.path.join(_HERE, "emul", "libnsemul.so")
     deps = [src] + [os.path.join(ROOT, "needlestack_b200", "csrc", f) for f in
-                    ("ns_math.cuh", "ns_quad.cuh", "ns_core.cuh")] + [os.path.join(ROOT, "include", "ns_b200.h")]
+                    ("ns_math.cuh", "ns_quad.cuh", "ns_core.cuh", "ns_fit.cuh")] + [os.path.join(ROOT, "include", "ns_b200.h")]
     if (not os.path.exists(out)) or any(os.path.getmtime(d) > os.path.getmtime(out) for d in deps):
         subprocess.run(["g++", "-O2", "-fPIC", "-shared", "-std=c++17", "-o", out, src], check=True)
     return out
@@ -73,7 +73,7 @@ def roles(n, pairs):
     return role
 
 
-def call_unit(dp, vp, vm, rp, rm, prm, pairs=None, is_indel=False, plain=False):
+def call_unit(dp, vp, vm, rp, rm, prm, pairs=None, is_indel=False, plain=False, fast=True):
     arrs = [np.ascontiguousarray(a, dtype=np.int32) for a in (dp, vp, vm, rp, rm)]
     n = len(arrs[0])
     out = {k: np.empty(n) for k in ("pvalue", "qvalue", "gq", "qval_minaf", "sor", "rvsb", "fs")}
@@ -82,9 +82,9 @@ def call_unit(dp, vp, vm, rp, rm, prm, pairs=None, is_indel=False, plain=False):
     pooled = np.zeros(8)
     sigma, slope, mg = C.c_double(), C.c_double(), C.c_double()
     flags, iters = C.c_uint32(), C.c_uint32()
-    cnt = (C.c_uint64 * 3)()
+    cnt = (C.c_uint64 * 4)()
     role = roles(n, pairs)
-    lib().emul_unit(n, *[a.ctypes.data_as(_abi.c_ip) for a in arrs], int(is_indel), int(plain), C.byref(prm),
+    lib().emul_unit(n, *[a.ctypes.data_as(_abi.c_ip) for a in arrs], int(is_indel), int(plain), int(fast), C.byref(prm),
                     role.ctypes.data_as(_abi.c_bp),
                     *[out[k].ctypes.data_as(_abi.c_dp) for k in ("pvalue", "qvalue", "gq", "qval_minaf", "sor",
                                                                   "rvsb", "fs")],
@@ -92,5 +92,5 @@ def call_unit(dp, vp, vm, rp, rm, prm, pairs=None, is_indel=False, plain=False):
                     C.byref(sigma), C.byref(slope), C.byref(mg), C.byref(flags), C.byref(iters), cnt)
     out.update(gt=gt, status=st, pooled=pooled, sigma=sigma.value, slope=slope.value, max_gq=mg.value,
                flags=flags.value, n_outer=iters.value & 0xff, n_irls=(iters.value >> 8) & 0x3ff,
-               n_obj=iters.value >> 18, n_seed=cnt[0], n_lattice=cnt[1], n_quad=cnt[2])
+               n_obj=iters.value >> 18, n_seed=cnt[0], n_lattice=cnt[1], n_quad=cnt[2], deferred=cnt[3])
     return out

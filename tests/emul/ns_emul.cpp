@@ -13,7 +13,7 @@ extern "C" {
 
 /* the same defaults as the library (duplicated on purpose: the emulation must not link it) */
 int emul_unit(int n, const int32_t *dp, const int32_t *vp, const int32_t *vm, const int32_t *rp,
-              const int32_t *rm, int is_indel, int plain, const ns_params *prm_in,
+              const int32_t *rm, int is_indel, int plain, int fast, const ns_params *prm_in,
               const uint8_t *role, double *pvalue, double *qvalue, double *gq, double *qval_minaf,
               double *sor, double *rvsb, double *fs, uint8_t *gt, uint8_t *status, double *pooled,
               double *sigma, double *slope, double *max_gq, uint32_t *flags_out, uint32_t *iters,
@@ -30,13 +30,16 @@ int emul_unit(int n, const int32_t *dp, const int32_t *vp, const int32_t *vm, co
     r.is_indel = is_indel;
     r.valid = 1;
     std::vector<double> buf(ns_work_doubles(n) + 3 * (size_t)n + 16);
+    static double rtab[NS_RTAB];
+    for (int j = 1; j < NS_RTAB; j++)
+        rtab[j] = 1.0 / (double)j;
     ns_work w;
-    ns_work_bind(w, buf.data(), n);
+    ns_work_bind(w, buf.data(), n, rtab);
     uint32_t flags = ns_gate_unit<SerialG>(r, n, prm, plain, w.scratch);
     *sigma = NAN;
     *slope = NAN;
     *iters = 0;
-    counters[0] = counters[1] = counters[2] = 0;
+    counters[0] = counters[1] = counters[2] = counters[3] = 0;
     if (!(flags & NS_F_GATED)) {
         const bool inv = flags & NS_F_REF_INV, extra = flags & NS_F_EXTRA_ROB;
         double maxmu = -INFINITY;
@@ -49,7 +52,21 @@ int emul_unit(int n, const int32_t *dp, const int32_t *vp, const int32_t *vm, co
             w.x[i] = keep ? x : 0.0;
         }
         ns_fit_result res;
-        ns_fit_unit<SerialG>(w, n, maxmu, prm, res);
+        if (fast)
+            ns_fit_unit<SerialG, 1>(w, n, maxmu, prm, res);
+        if (!fast || res.deferred) { /* the warp kernel hands such units to the heavy kernel */
+            for (int i = 0; i < n; i++) {
+                double x = ns_ld(dp, i);
+                double y = inv ? ns_ld(rp, i) + ns_ld(rm, i) : ns_ld(vp, i) + ns_ld(vm, i);
+                bool keep = !(extra && y / x > prm.min_af_extra_rob);
+                w.y[i] = y;
+                w.x[i] = keep ? x : 0.0;
+            }
+            int was_deferred = fast ? res.deferred : 0;
+            ns_fit_unit<SerialG, 0>(w, n, maxmu, prm, res);
+            res.deferred = was_deferred;
+        }
+        counters[3] = (uint64_t)res.deferred;
         flags |= res.flags;
         *sigma = res.sigma;
         *slope = res.slope;

@@ -22,7 +22,7 @@ def snv_unit_rows(ref, counts, u):
     return c[0], c[1 + a], c[5 + a], c[1 + r], c[5 + r]
 
 
-def emul_snv_batch(emul, ref, counts, prm, pairs=None):
+def emul_snv_batch(emul, ref, counts, prm, pairs=None, fast=True):
     P, _, n = counts.shape
     U = 3 * P
     keys_d = ("pvalue", "qvalue", "gq", "qval_minaf", "sor", "rvsb", "fs")
@@ -38,7 +38,7 @@ def emul_snv_batch(emul, ref, counts, prm, pairs=None):
         if ref[u // 3] > 3:
             out["flags"][u] = _abi.NS_F_SKIPPED | _abi.NS_F_GATED
             continue
-        E = emul.call_unit(*snv_unit_rows(ref, counts, u), prm, pairs=pairs)
+        E = emul.call_unit(*snv_unit_rows(ref, counts, u), prm, pairs=pairs, fast=fast)
         for k in keys_d + ("gt", "status", "pooled"):
             out[k][u] = E[k]
         for k in ("sigma", "slope", "max_gq", "flags", "n_outer", "n_irls", "n_obj"):
