@@ -387,6 +387,43 @@ static cudaError_t ns_reserve_units(ns_ctx *ctx, size_t U)
     return ctx->cub_tmp.reserve(tmp + 256);
 }
 
+/* cluster launch of k_fit_heavy: CL CTAs per unit, as many clusters as can be co-resident */
+static cudaError_t ns_launch_heavy(ns_ctx *ctx, cudaStream_t st, int n, int n_units_max, size_t smh, const ns_unit_src &src,
+                                   const ns_params &dprm, int64_t u0, const ns_unit_arrays &ua, int which)
+{
+    const int wpc = NS_HEAVY_THREADS / 32;
+    int cl = 1;
+    while (cl < 8 && cl * wpc < n)
+        cl <<= 1; /* enough warps for one sample per warp, up to the portable cluster size 8 */
+    const char *ecl = getenv("NS_HEAVY_CLUSTER");
+    if (ecl && atoi(ecl) >= 1 && atoi(ecl) <= 8)
+        cl = atoi(ecl);
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.blockDim = dim3(NS_HEAVY_THREADS);
+    cfg.dynamicSmemBytes = smh;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = cl;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cfg.gridDim = dim3(cl);
+    int ncl = 0;
+    cudaError_t e = cudaOccupancyMaxActiveClusters(&ncl, k_fit_heavy, &cfg);
+    if (e != cudaSuccess)
+        return e;
+    if (ncl < 1)
+        ncl = 1;
+    if (ncl > n_units_max)
+        ncl = n_units_max;
+    cfg.gridDim = dim3(cl * ncl);
+    ns_counters *cp = ctx->counters.p;
+    return cudaLaunchKernelEx(&cfg, k_fit_heavy, src, dprm, u0, ua, cp, which);
+}
+
 static float ev_ms(cudaEvent_t a, cudaEvent_t b)
 {
     float ms = 0;
@@ -455,9 +492,7 @@ static int ns_run_chunk(ns_ctx *ctx, const ns_params &dprm, const double *qtab, 
         CK(cudaEventRecord(ctx->ev_fork, st));
         CK(cudaStreamWaitEvent(ctx->heavy_stream, ctx->ev_fork, 0));
         CK(cudaEventRecord(ctx->ev_h0, ctx->heavy_stream));
-        int hblocks = n_pre < ctx->sm_count ? n_pre : ctx->sm_count;
-        k_fit_heavy<<<hblocks, hthreads, smh, ctx->heavy_stream>>>(src, dprm, u0_src, ua, ctx->counters.p, 0);
-        CK(cudaGetLastError());
+        CK(ns_launch_heavy(ctx, ctx->heavy_stream, n, n_pre, smh, src, dprm, u0_src, ua, 0));
         CK(cudaEventRecord(ctx->ev_h1, ctx->heavy_stream));
         CK(cudaEventRecord(ctx->ev_join, ctx->heavy_stream));
         heavy_forked = true;
@@ -490,9 +525,7 @@ static int ns_run_chunk(ns_ctx *ctx, const ns_params &dprm, const double *qtab, 
         CK(cudaStreamWaitEvent(st, ctx->ev_join, 0));
     if (n_light > 0) {
         /* handed over by the warp kernel (count is on the device: a few CTAs that exit at once if none) */
-        int hblocks = n_light < ctx->sm_count ? n_light : ctx->sm_count;
-        k_fit_heavy<<<hblocks, hthreads, smh, st>>>(src, dprm, u0_src, ua, ctx->counters.p, 1);
-        CK(cudaGetLastError());
+        CK(ns_launch_heavy(ctx, st, n, n_light < 64 ? n_light : 64, smh, src, dprm, u0_src, ua, 1));
         ctx->tm.kernel_launches++;
     }
     CK(cudaEventRecord(ctx->ev[3], st));

@@ -98,6 +98,12 @@ struct WarpG {
         }
         __syncwarp();
     }
+    /* replica-local variants (identical to the group-wide ones unless the group spans CTAs) */
+    __device__ static __forceinline__ int lnl() { return nl(); }
+    __device__ static __forceinline__ int llane() { return lane(); }
+    __device__ static __forceinline__ double lsum(double v) { return sum(v); }
+    __device__ static __forceinline__ int lisum(int v) { return isum(v); }
+    __device__ static __forceinline__ void lsync() { sync(); }
 };
 
 /* one CTA = one unit, one WARP = one "lane" of the group (the heavy kernel): the values handed to
@@ -139,6 +145,95 @@ struct CoopG {
     __device__ static __forceinline__ int isum(int v) { return (int)sum((double)v); }
     __device__ static __forceinline__ int any(int p) { return __syncthreads_or(p); }
     __device__ static __forceinline__ void sync() { __syncthreads(); }
+    __device__ static __forceinline__ void fill_dtab(double *, double, int) {}
+    /* replica-local variants (identical to the group-wide ones unless the group spans CTAs) */
+    __device__ static __forceinline__ int lnl() { return nl(); }
+    __device__ static __forceinline__ int llane() { return lane(); }
+    __device__ static __forceinline__ double lsum(double v) { return sum(v); }
+    __device__ static __forceinline__ int lisum(int v) { return isum(v); }
+    __device__ static __forceinline__ void lsync() { sync(); }
+};
+
+/* one thread-block CLUSTER = one unit: every CTA keeps a replica of the unit's per-sample state in
+ * its own shared memory, the samples of the expensive window loops are split over all warps of
+ * the cluster, and the partial sums are exchanged through distributed shared memory
+ * (cluster.map_shared_rank) with one barrier.cluster per reduction (double-buffered slots).
+ * Values handed to the collectives are uniform within each warp. */
+struct ClusterG {
+    __device__ static __forceinline__ unsigned crank()
+    {
+        unsigned r;
+        asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+        return r;
+    }
+    __device__ static __forceinline__ unsigned csize()
+    {
+        unsigned r;
+        asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r));
+        return r;
+    }
+    __device__ static __forceinline__ void csync()
+    {
+        asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+    }
+    /* store v into slot `slot` of the exchange array of CTA `rank` */
+    __device__ static __forceinline__ void remote_store(double *local_ptr, unsigned rank, double v)
+    {
+        unsigned a = (unsigned)__cvta_generic_to_shared(local_ptr), ra;
+        asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(a), "r"(rank));
+        asm volatile("st.shared::cluster.f64 [%0], %1;" ::"r"(ra), "d"(v) : "memory");
+    }
+    __device__ static __forceinline__ void remote_store_int(int *local_ptr, unsigned rank, int v)
+    {
+        unsigned a = (unsigned)__cvta_generic_to_shared(local_ptr), ra;
+        asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(a), "r"(rank));
+        asm volatile("st.shared::cluster.u32 [%0], %1;" ::"r"(ra), "r"(v) : "memory");
+    }
+    __device__ static __forceinline__ double *xch()
+    {
+        __shared__ double x[2][16];
+        return &x[0][0];
+    }
+    __device__ static __forceinline__ int &phase()
+    {
+        __shared__ int ph;
+        return ph;
+    }
+    __device__ static __forceinline__ int nl() { return (int)csize() * (blockDim.x >> 5); }
+    __device__ static __forceinline__ int lane() { return (int)crank() * (blockDim.x >> 5) + (threadIdx.x >> 5); }
+    __device__ static __forceinline__ int lnl() { return blockDim.x >> 5; }
+    __device__ static __forceinline__ int llane() { return threadIdx.x >> 5; }
+    __device__ static __forceinline__ double lsum(double v) { return CoopG::sum(v); }
+    __device__ static __forceinline__ int lisum(int v) { return CoopG::isum(v); }
+    __device__ static __forceinline__ void lsync() { __syncthreads(); }
+    __device__ static __forceinline__ void sync() { __syncthreads(); }
+    /* OP 0: sum, 1: max */
+    template <int OP> __device__ static __forceinline__ double allreduce(double v)
+    {
+        double p = OP == 0 ? CoopG::sum(v) : CoopG::max(v); /* CTA partial, uniform in the CTA */
+        const unsigned cs = csize();
+        if (cs == 1)
+            return p;
+        /* every thread knows the parity: it toggles once per call, uniformly */
+        int &ph = phase();
+        const int par = ph & 1;
+        double *x = xch() + par * 16;
+        if (threadIdx.x < cs)
+            remote_store(x + crank(), threadIdx.x, p);
+        csync();
+        double t = OP == 0 ? 0.0 : -INFINITY;
+        for (unsigned k = 0; k < cs; k++)
+            t = OP == 0 ? t + x[k] : fmax(t, x[k]);
+        __syncthreads();
+        if (threadIdx.x == 0)
+            ph = par ^ 1;
+        __syncthreads();
+        return t;
+    }
+    __device__ static __forceinline__ double sum(double v) { return allreduce<0>(v); }
+    __device__ static __forceinline__ double max(double v) { return allreduce<1>(v); }
+    __device__ static __forceinline__ int isum(int v) { return (int)sum((double)v); }
+    __device__ static __forceinline__ int any(int p) { return sum(__syncthreads_or(p) ? 1.0 : 0.0) > 0.0; }
     __device__ static __forceinline__ void fill_dtab(double *, double, int) {}
 };
 
@@ -183,6 +278,12 @@ struct BlockG {
     __device__ static __forceinline__ int any(int p) { return __syncthreads_or(p); }
     __device__ static __forceinline__ void sync() { __syncthreads(); }
     __device__ static __forceinline__ void fill_dtab(double *, double, int) {}
+    /* replica-local variants (identical to the group-wide ones unless the group spans CTAs) */
+    __device__ static __forceinline__ int lnl() { return nl(); }
+    __device__ static __forceinline__ int llane() { return lane(); }
+    __device__ static __forceinline__ double lsum(double v) { return sum(v); }
+    __device__ static __forceinline__ int lisum(int v) { return isum(v); }
+    __device__ static __forceinline__ void lsync() { sync(); }
 };
 #define NS_GD __device__
 #else
@@ -211,6 +312,12 @@ struct SerialG {
             acc += 1.0 / (a + (double)j);
         }
     }
+    /* replica-local variants (identical to the group-wide ones unless the group spans CTAs) */
+    static NS_HD int lnl() { return nl(); }
+    static NS_HD int llane() { return lane(); }
+    static NS_HD double lsum(double v) { return sum(v); }
+    static NS_HD int lisum(int v) { return isum(v); }
+    static NS_HD void lsync() { sync(); }
 };
 
 #if defined(__CUDACC__)

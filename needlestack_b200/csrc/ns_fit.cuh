@@ -571,8 +571,8 @@ NS_GF inline double ns_irls_step(double sig, const ns_work &w, int n, double max
     if (G::any(nanrows))
         res.flags |= NS_F_NAN_ROWS;
     const double beta = swz / sw;
-    G::sync();
-    for (int i = lane; i < n; i += G::nl()) {
+    G::lsync();
+    for (int i = G::llane(); i < n; i += G::lnl()) { /* every replica updates all samples */
         if (!(w.x[i] > 0))
             continue;
         double mu = exp(w.X[i] + beta);
@@ -583,7 +583,7 @@ NS_GF inline double ns_irls_step(double sig, const ns_work &w, int n, double max
         w.mu[i] = mu;
         w.eta[i] = log(mu);
     }
-    G::sync();
+    G::lsync();
     return beta;
 }
 
@@ -593,7 +593,7 @@ NS_GF inline double ns_irls_step(double sig, const ns_work &w, int n, double max
 template <class G, int MODE>
 NS_GF inline void ns_fit_unit(const ns_work &w, int n, double maxmu, const ns_params &prm, ns_fit_result &res)
 {
-    const int lane = G::lane();
+    const int lane = G::llane(); /* the initial estimates are computed by every replica */
     res.flags = 0;
     res.n_outer = res.n_irls = res.n_obj = 0;
     res.deferred = 0;
@@ -603,7 +603,7 @@ NS_GF inline void ns_fit_unit(const ns_work &w, int n, double maxmu, const ns_pa
     /* :58-63, :75-76 */
     int nfit = 0;
     double sum_ex = 0;
-    for (int i = lane; i < n; i += G::nl()) {
+    for (int i = lane; i < n; i += G::lnl()) {
         double x = w.x[i];
         if (x > 0) {
             double X = log(x);
@@ -615,14 +615,14 @@ NS_GF inline void ns_fit_unit(const ns_work &w, int n, double maxmu, const ns_pa
             nfit++;
         }
     }
-    nfit = G::isum(nfit);
-    sum_ex = G::sum(sum_ex);
-    G::sync();
+    nfit = G::lisum(nfit);
+    sum_ex = G::lsum(sum_ex);
+    G::lsync();
     /* :77 type-7 quartiles of af by rank counting */
     const double h25 = (double)(nfit - 1) * 0.25, h75 = (double)(nfit - 1) * 0.75;
     const int lo25 = (int)floor(h25), hi25 = (int)ceil(h25), lo75 = (int)floor(h75), hi75 = (int)ceil(h75);
     double v0 = 0, v1 = 0, v2 = 0, v3 = 0;
-    for (int i = lane; i < n; i += G::nl()) {
+    for (int i = lane; i < n; i += G::lnl()) {
         if (!(w.x[i] > 0))
             continue;
         double ai = w.eta[i];
@@ -640,10 +640,10 @@ NS_GF inline void ns_fit_unit(const ns_work &w, int n, double maxmu, const ns_pa
         if (rank == hi75)
             v3 = ai;
     }
-    v0 = G::sum(v0);
-    v1 = G::sum(v1);
-    v2 = G::sum(v2);
-    v3 = G::sum(v3);
+    v0 = G::lsum(v0);
+    v1 = G::lsum(v1);
+    v2 = G::lsum(v2);
+    v3 = G::lsum(v3);
     double q25 = v0, q75 = v2;
     if (h25 > (double)lo25 && v1 != v0) {
         double h = h25 - (double)lo25;
@@ -656,23 +656,23 @@ NS_GF inline void ns_fit_unit(const ns_work &w, int n, double maxmu, const ns_pa
     const double fence = q75 + 1.5 * (q75 - q25);
     double s_af = 0;
     int c_af = 0;
-    for (int i = lane; i < n; i += G::nl())
+    for (int i = lane; i < n; i += G::lnl())
         if (w.x[i] > 0 && w.eta[i] <= fence) {
             s_af += w.eta[i];
             c_af++;
         }
-    s_af = G::sum(s_af);
-    c_af = G::isum(c_af);
+    s_af = G::lsum(s_af);
+    c_af = G::lisum(c_af);
     double inislope = s_af / (double)c_af;
     {
         double mean_ex = sum_ex / (double)nfit;
         if (inislope <= 1 / (10 * mean_ex))
             inislope = 1 / (10 * mean_ex); /* :78 */
     }
-    G::sync();
+    G::lsync();
     /* :79-86 */
     double s_sig = 0;
-    for (int i = lane; i < n; i += G::nl()) {
+    for (int i = lane; i < n; i += G::lnl()) {
         if (!(w.x[i] > 0))
             continue;
         double mu = inislope * exp(w.X[i]);
@@ -685,13 +685,13 @@ NS_GF inline void ns_fit_unit(const ns_work &w, int n, double maxmu, const ns_pa
         double t = w.y[i] / mu - 1;
         s_sig += t * t;
     }
-    s_sig = G::sum(s_sig);
+    s_sig = G::lsum(s_sig);
     double sig = s_sig / (double)nfit;
     if (sig > prm.maxsig)
         sig = prm.maxsig;
     if (sig < prm.minsig)
         sig = prm.minsig;
-    G::sync();
+    G::lsync();
 
     /* :166-205 alternation */
     const double tol = prm.tol;

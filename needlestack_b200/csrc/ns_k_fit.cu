@@ -92,7 +92,9 @@ k_fit(ns_unit_src src, ns_params prm, int64_t u0, ns_unit_arrays ua, ns_counters
     }
 }
 
-/* one CTA per unit; warps take samples, lanes share each sample's window (ns_coop.cuh) */
+/* One thread-block cluster per unit: the CTAs of the cluster split the unit's samples, every
+ * warp takes one sample at a time and its lanes share that sample's window (ns_coop.cuh); sums
+ * over samples are exchanged through distributed shared memory (ClusterG). */
 __global__ void __launch_bounds__(NS_HEAVY_THREADS, 1)
 k_fit_heavy(ns_unit_src src, ns_params prm, int64_t u0, ns_unit_arrays ua, ns_counters *cnt, int which)
 {
@@ -103,6 +105,8 @@ k_fit_heavy(ns_unit_src src, ns_params prm, int64_t u0, ns_unit_arrays ua, ns_co
     double *rt = ns_smem;
     for (int j = threadIdx.x; j < NS_RTAB_HEAVY; j += blockDim.x)
         rt[j] = j > 0 ? 1.0 / (double)j : 0.0;
+    if (threadIdx.x == 0)
+        ClusterG::phase() = 0;
     ns_work w;
     ns_work_bind(w, ns_smem + NS_RTAB_HEAVY, n, rt);
     double *cs = ns_smem + NS_RTAB_HEAVY + ns_work_doubles(n) + (size_t)warp * NS_COOP_DOUBLES;
@@ -117,11 +121,16 @@ k_fit_heavy(ns_unit_src src, ns_params prm, int64_t u0, ns_unit_arrays ua, ns_co
     const int n_heavy = which ? cnt->n_heavy : cnt->n_pre;
     int *next = which ? &cnt->next_heavy : &cnt->next_pre;
     const int *list = which ? ua.heavy_list : ua.pre_list;
+    const unsigned crank = ClusterG::crank(), csize = ClusterG::csize();
+    __syncthreads();
     for (;;) {
-        __syncthreads();
-        if (threadIdx.x == 0)
-            s_idx = atomicAdd(next, 1);
-        __syncthreads();
+        ClusterG::csync(); /* the previous unit is finished everywhere, s_idx may be overwritten */
+        if (crank == 0 && threadIdx.x == 0) {
+            int idx = atomicAdd(next, 1);
+            for (unsigned r = 0; r < csize; r++)
+                ClusterG::remote_store_int(&s_idx, r, idx);
+        }
+        ClusterG::csync();
         const int idx = s_idx;
         if (idx >= n_heavy)
             break;
@@ -134,13 +143,13 @@ k_fit_heavy(ns_unit_src src, ns_params prm, int64_t u0, ns_unit_arrays ua, ns_co
         maxmu = BlockG::max(maxmu);
         __syncthreads();
         ns_fit_result res;
-        ns_fit_unit<CoopG, 2>(w, n, maxmu, prm, res);
-        if (lane == 0) { /* counters are uniform within a warp */
+        ns_fit_unit<ClusterG, 2>(w, n, maxmu, prm, res);
+        if (lane == 0) { /* counters are uniform within a warp, disjoint across warps and CTAs */
             tot_seed += res.cnt.n_seed;
             tot_lat += res.cnt.n_lattice;
             tot_quad += res.cnt.n_quad;
         }
-        if (threadIdx.x == 0)
+        if (crank == 0 && threadIdx.x == 0)
             ns_store_fit(ua, u, flags, res, t_start);
     }
     tot_seed = (unsigned long long)BlockG::sum((double)tot_seed);
