@@ -536,7 +536,7 @@ static int ns_run_chunk(ns_ctx *ctx, const ns_params &dprm, const double *qtab, 
         size_t per_warp = (3 * (size_t)n + 8) * sizeof(double);
         while (wpb > 1 && wpb * per_warp > 200 * 1024)
             wpb >>= 1;
-        size_t sm = wpb * per_warp;
+        size_t sm = NS_RTAB * sizeof(double) + wpb * per_warp;
         if (sm > 48 * 1024)
             CK(cudaFuncSetAttribute(k_post, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
         int bps = 0;

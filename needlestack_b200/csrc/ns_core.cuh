@@ -539,6 +539,36 @@ NS_HD double ns_holm_last(double pstar, const double *srt, const double *hmax, i
     return v < 1 ? v : 1;
 }
 
+/* fisher.test(2x2) for the POOLED table (needlestack.r:236): the support can hold thousands of
+ * terms, so the lanes of the group split it into contiguous chunks; each lane seeds its chunk
+ * with one Loader evaluation relative to the mode and walks it by the ratio recurrence. */
+template <class G> NS_GF inline double ns_fisher_pooled(double a11, double a21, double a12, double a22)
+{
+    const double m = a11 + a21, n = a12 + a22, k = a11 + a12, x = a11;
+    const double lo = fmax(0.0, k - n), hi = fmin(k, m);
+    if (hi <= lo)
+        return 1.0;
+    const double ns = hi - lo + 1;
+    if (G::nl() == 1 || ns < 256)
+        return ns_fisher_2x2_ool(a11, a21, a12, a22);
+    const double mode = ns_hyper_mode(m, n, k, lo, hi);
+    const double lmode = ns_dhyper_log(mode, m, n, k);
+    const double per = ceil(ns / (double)G::nl());
+    const double a = lo + (double)G::lane() * per, b = fmin(hi, a + per - 1);
+    double dobs = 0, dummy = 0, tot = 0, dstart = 0;
+    const bool have = a <= hi;
+    if (have) {
+        dstart = exp(ns_dhyper_log(a, m, n, k) - lmode);
+        tot = ns_hyper_walk(a, b, a, dstart, m, n, k, -1.0, x, dobs);
+    }
+    tot = G::sum(tot);
+    dobs = G::sum(dobs); /* exactly one lane visited x */
+    const double thr = dobs * (1 + 1e-7);
+    double pv = have ? ns_hyper_walk(a, b, a, dstart, m, n, k, thr, -1.0, dummy) : 0.0;
+    pv = G::sum(pv);
+    return pv / tot;
+}
+
 /* Per-unit tail: p-values, BH q-values, GQ (glm_rob_nb.r:219-224); power q-values and
  * tumour/normal status (needlestack.r:340-380); gate 1, strand bias, gate 2, genotype
  * (needlestack.r:381-409).  sm: group-shared scratch of >= 3n+8 doubles.
@@ -546,7 +576,8 @@ NS_HD double ns_holm_last(double pstar, const double *srt, const double *hmax, i
 template <class G>
 NS_GF inline uint32_t ns_post_unit(const ns_rows &r, int n, const ns_params &prm, uint32_t flags,
                                    double sigma, double slope, const double *qtab, int qtab_len,
-                                   const ns_unit_out &o, double *sm, double &max_gq_out)
+                                   const ns_unit_out &o, double *sm, double &max_gq_out,
+                                   const double *rt = nullptr, int rtn = 0)
 {
     const int lane = G::lane();
     const bool gated = flags & NS_F_GATED;
@@ -567,7 +598,7 @@ NS_GF inline uint32_t ns_post_unit(const ns_rows &r, int n, const ns_params &prm
         for (int i = lane; i < n; i += G::nl()) {
             double x = ns_ld(r.dp, i);
             double y = inv ? ns_ld(r.rp, i) + ns_ld(r.rm, i) : ns_ld(r.vp, i) + ns_ld(r.vm, i);
-            double p = ns_nb_pvalue(y, size, slope * x);
+            double p = ns_nb_pvalue(y, size, slope * x, rt, rtn);
             o.pvalue[i] = p;
             tmp[i] = p;
         }
@@ -671,11 +702,11 @@ NS_GF inline uint32_t ns_post_unit(const ns_rows &r, int n, const ns_params &prm
         double ystar;
         if (kind == 1) {
             int xi = (int)x;
-            ystar = (qtab && xi < qtab_len) ? qtab[xi] : ns_qnbinom_mu(0.01, 1 / prm.sigma_normal, 0.5 * x);
+            ystar = (qtab && xi < qtab_len) ? qtab[xi] : ns_qnbinom_mu_ool(0.01, 1 / prm.sigma_normal, 0.5 * x);
         } else {
-            ystar = ns_qbinom(0.01, x, afmin);
+            ystar = ns_qbinom_ool(0.01, x, afmin);
         }
-        double pstar = ns_nb_pvalue(ystar, size, slope * x);
+        double pstar = ns_nb_pvalue(ystar, size, slope * x, rt, rtn);
         o.qval_minaf[i] = -10 * log10(ns_holm_last(pstar, srt, hm, n));
     }
     G::sync();
@@ -766,7 +797,7 @@ NS_GF inline uint32_t ns_post_unit(const ns_rows &r, int n, const ns_params &prm
         else if (fabs(s) > NS_DBL_MAX)
             s = 99;
         o.sor[i] = s;
-        o.fs[i] = -10 * log10(ns_fisher_2x2(Vp, Vm, Rp, Rm)); /* the cap at :235 is a no-op */
+        o.fs[i] = -10 * log10(ns_fisher_2x2_ool(Vp, Vm, Rp, Rm)); /* the cap at :235 is a no-op */
         sVp += Vp;
         sVm += Vm;
         sRp += Rp;
@@ -788,10 +819,11 @@ NS_GF inline uint32_t ns_post_unit(const ns_rows &r, int n, const ns_params &prm
             as = -1;
         else if (fabs(as) > NS_DBL_MAX)
             as = 99;
+        const double fs_all = -10 * log10(ns_fisher_pooled<G>(sVp, sVm, sRp, sRm));
         if (lane == 0) {
             o.pooled[0] = as;
             o.pooled[1] = ar;
-            o.pooled[2] = -10 * log10(ns_fisher_2x2(sVp, sVm, sRp, sRm));
+            o.pooled[2] = fs_all;
             o.pooled[3] = sRp;
             o.pooled[4] = sRm;
             o.pooled[5] = sVp;

@@ -3,12 +3,17 @@
 
 extern __shared__ double ns_smem[];
 
-__global__ void k_post(ns_unit_src src, ns_params prm, int64_t u0, ns_unit_arrays ua, ns_planes pl,
+__global__ void __launch_bounds__(128, 4)
+k_post(ns_unit_src src, ns_params prm, int64_t u0, ns_unit_arrays ua, ns_planes pl,
                        const double *qtab, int qtab_len, ns_counters *cnt)
 {
     const int n = src.n;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    double *sm = ns_smem + (size_t)warp * (3 * (size_t)n + 8);
+    double *rtab = ns_smem; /* CTA-shared 1/j, j < NS_RTAB */
+    for (int j = threadIdx.x; j < NS_RTAB; j += blockDim.x)
+        rtab[j] = j > 0 ? 1.0 / (double)j : 0.0;
+    __syncthreads();
+    double *sm = ns_smem + NS_RTAB + (size_t)warp * (3 * (size_t)n + 8);
     const int n_post = cnt->n_post;
     for (;;) {
         int idx = 0;
@@ -35,7 +40,7 @@ __global__ void k_post(ns_unit_src src, ns_params prm, int64_t u0, ns_unit_array
             o.pooled[lane] = NAN;
         double mg = 0;
         uint32_t flags = ns_post_unit<WarpG>(r, n, prm, ua.flags[u], ua.sigma[u], ua.slope[u], qtab, qtab_len,
-                                             o, sm, mg);
+                                             o, sm, mg, rtab, NS_RTAB);
         if (lane == 0) {
             ua.flags[u] = flags;
             ua.max_gq[u] = mg;

@@ -284,10 +284,54 @@ NS_HD double ns_pbinom_lower(double q, double n, double p)
     return ns_pbeta_raw(p, 1.0 - p, q + 1.0, n - q, 0);
 }
 
-/* P(Y >= y) = dnbinom(y) + pnbinom(y, lower=F): the p-value of glm_rob_nb.r:221 */
-NS_HD double ns_nb_pvalue(double y, double size, double mu)
+/* continued-fraction tail kept out of line: the callers' hot path is the direct sum below */
+#if defined(__CUDACC__)
+static __host__ __device__ __noinline__ double ns_nb_pvalue_cf(double y, double size, double mu)
+#else
+static double ns_nb_pvalue_cf(double y, double size, double mu)
+#endif
 {
     return ns_dnbinom_mu(y, size, mu) + ns_pnbinom_mu_upper(y, size, mu);
+}
+
+/* P(Y >= y) = dnbinom(y) + pnbinom(y, lower=F): the p-value of glm_rob_nb.r:221 and the power
+ * p-value of needlestack.r:244-245,250-251.
+ * When the pmf ratio (j+size)/(j+1) * mu/(mu+size) is safely below 1 from y on (error-level
+ * means: every sample of an exome panel) the tail is summed directly by the pmf recurrence from
+ * pmf(0) = (1+mu/size)^(-size): 1 - sum_{j<y} when that is not a cancellation, else sum_{j>=y}
+ * until the terms drop below 1e-17 of the sum.  Otherwise the continued fraction above.
+ * rt: optional table of 1/j (j < rtn). */
+NS_HD double ns_nb_pvalue(double y, double size, double mu, const double *rt = nullptr, int rtn = 0)
+{
+    if (y <= 0)
+        return 1.0;
+    if (!(mu > 0))
+        return (mu == 0) ? 0.0 : NAN; /* mu == 0 (depth 0) and y > 0; NaN propagates */
+    const double q = mu / (mu + size);
+    const double r_y = ((y + size) / (y + 1)) * q;
+    if (mu < 500.0 && y < 4096.0 && fmax(r_y, q) < 0.9) {
+        double pm = exp(-size * log1p(mu / size));
+        double S = 0.0, j = 0.0;
+        for (; j < y; j += 1) {
+            S += pm;
+            double ij = (rt && j + 1 < (double)rtn) ? rt[(int)j + 1] : 1.0 / (j + 1);
+            pm *= ((j + size) * ij) * q;
+        }
+        if (S < 0.5)
+            return 1.0 - S;
+        double T = 0.0;
+        for (int it = 0; it < 4096; it++) {
+            T += pm;
+            const double t = pm;
+            double ij = (rt && j + 1 < (double)rtn) ? rt[(int)j + 1] : 1.0 / (j + 1);
+            pm *= ((j + size) * ij) * q;
+            j += 1;
+            if (t <= 1e-17 * T)
+                break;
+        }
+        return T;
+    }
+    return ns_nb_pvalue_cf(y, size, mu);
 }
 
 /* ---------------------------------------------------------------------------------
@@ -412,24 +456,66 @@ NS_HD double ns_dhyper_log(double x, double r, double b, double n)
            ns_dbinom_raw_log(n, r + b, p, q);
 }
 
+/* hypergeometric pmf ratio d(s+1)/d(s) for dhyper(s, m, n, k) */
+NS_HD double ns_hyper_up(double s, double m, double n, double k)
+{
+    return ((m - s) * (k - s)) / ((s + 1) * (n - k + s + 1));
+}
+
+/* sum of the densities (relative to the mode) over [a, b] (a <= b inside the support), walking
+ * away from `from` whose relative density is d_from; returns also the density at x if visited.
+ * thr < 0: plain sum; thr >= 0: only terms <= thr are added. */
+NS_HD double ns_hyper_walk(double a, double b, double from, double d_from, double m, double n, double k, double thr,
+                           double x, double &d_at_x)
+{
+    double acc = 0;
+    if (from <= a) { /* upward a..b starting at a == from */
+        double d = d_from;
+        for (double s = a; s <= b; s += 1) {
+            if (s == x)
+                d_at_x = d;
+            if (thr < 0 || d <= thr)
+                acc += d;
+            d *= ns_hyper_up(s, m, n, k);
+        }
+    } else { /* downward b..a starting at b == from */
+        double d = d_from;
+        for (double s = b; s >= a; s -= 1) {
+            if (s == x)
+                d_at_x = d;
+            if (thr < 0 || d <= thr)
+                acc += d;
+            d /= ns_hyper_up(s - 1, m, n, k);
+        }
+    }
+    return acc;
+}
+
+NS_HD double ns_hyper_mode(double m, double n, double k, double lo, double hi)
+{
+    double mode = floor((k + 1) * (m + 1) / (m + n + 2));
+    return fmin(fmax(mode, lo), hi);
+}
+
+/* lane-local version: densities relative to the mode by the ratio recurrence (the observed
+ * table's density and every term the 1e-7 slack of R's comparison can matter for are exact to
+ * ~support*eps); terms that underflow relative to the mode are below 1e-308 of the total */
 NS_HD double ns_fisher_2x2(double a11, double a21, double a12, double a22)
 {
-    double m = a11 + a21, n = a12 + a22, k = a11 + a12, x = a11;
-    double lo = fmax(0.0, k - n), hi = fmin(k, m);
-    double mx = -INFINITY;
-    for (double s = lo; s <= hi; s += 1)
-        mx = fmax(mx, ns_dhyper_log(s, m, n, k));
-    double sum = 0;
-    for (double s = lo; s <= hi; s += 1)
-        sum += exp(ns_dhyper_log(s, m, n, k) - mx);
-    double dobs = (exp(ns_dhyper_log(x, m, n, k) - mx) / sum) * (1 + 1e-7);
-    double pv = 0;
-    for (double s = lo; s <= hi; s += 1) {
-        double d = exp(ns_dhyper_log(s, m, n, k) - mx) / sum;
-        if (d <= dobs)
-            pv += d;
-    }
-    return pv;
+    const double m = a11 + a21, n = a12 + a22, k = a11 + a12, x = a11;
+    const double lo = fmax(0.0, k - n), hi = fmin(k, m);
+    if (hi <= lo)
+        return 1.0;
+    const double mode = ns_hyper_mode(m, n, k, lo, hi);
+    double dobs = (x == mode) ? 1.0 : 0.0, dummy = 0;
+    double tot = ns_hyper_walk(mode, hi, mode, 1.0, m, n, k, -1.0, x, dobs);
+    if (mode > lo)
+        tot += ns_hyper_walk(lo, mode - 1, mode - 1, 1.0 / ns_hyper_up(mode - 1, m, n, k), m, n, k, -1.0, x, dobs);
+    const double thr = dobs * (1 + 1e-7);
+    double pv = ns_hyper_walk(mode, hi, mode, 1.0, m, n, k, thr, -1.0, dummy);
+    if (mode > lo)
+        pv += ns_hyper_walk(lo, mode - 1, mode - 1, 1.0 / ns_hyper_up(mode - 1, m, n, k), m, n, k, thr, -1.0, dummy);
+    return pv / tot;
 }
 
 /* SOR() of needlestack.r:206-215; IEEE arithmetic reproduces R's NaN / Inf cases */
@@ -443,3 +529,13 @@ NS_HD double ns_sor(double RO_f, double AO_f, double RO_r, double AO_r)
 /* R's pmax/pmin propagate NaN (fmax/fmin do not): used where an operand can be NaN */
 NS_HD double ns_rmax(double a, double b) { return (a != a || b != b) ? NAN : fmax(a, b); }
 NS_HD double ns_rmin(double a, double b) { return (a != a || b != b) ? NAN : fmin(a, b); }
+
+/* out-of-line entry points for code that is rarely reached from a hot kernel */
+#if defined(__CUDACC__)
+#define NS_OOL static __host__ __device__ __noinline__
+#else
+#define NS_OOL static
+#endif
+NS_OOL double ns_fisher_2x2_ool(double a, double b, double c, double d) { return ns_fisher_2x2(a, b, c, d); }
+NS_OOL double ns_qnbinom_mu_ool(double p, double size, double mu) { return ns_qnbinom_mu(p, size, mu); }
+NS_OOL double ns_qbinom_ool(double p, double n, double pr) { return ns_qbinom(p, n, pr); }
