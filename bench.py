@@ -404,6 +404,8 @@ def main():
                 "detail": {"site_alleles_processed_per_s": units_all / (ms_max * 1e-3),
                            "gate_pass_fraction": fitted_all / units_all, "fitted_per_step_rank0": R.n_fitted,
                            "emitted_per_step_rank0": n_emitted,
+                           "heavy_units_per_step_rank0": tm_sum.get("n_heavy", 0) / a.steps,
+                           "heavy_units_not_predicted_per_step_rank0": tm_sum.get("n_deferred", 0) / a.steps,
                            "kernel_ms_per_step_rank0": {k: v / a.steps for k, v in tm_sum.items()
                                                         if k.endswith("_ms")}}}
         print(json.dumps(line))

@@ -125,6 +125,7 @@ typedef struct ns_timings {
     double fit_phase_ms; /* wall time of the whole fit phase (both streams) */
     int64_t kernel_launches;
     int64_t n_heavy; /* units that took the spline + quadrature kernel */
+    int64_t n_deferred; /* ... of which the warp kernel handed over (not predicted by the gate kernel) */
     uint64_t fast_seed, fast_lattice; /* work counters of the warp kernel alone (k_fit) */
 } ns_timings;
 

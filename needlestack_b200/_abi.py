@@ -64,7 +64,7 @@ class NsOut(C.Structure):
 
 class NsTimings(C.Structure):
     _fields_ = [(k, C.c_double) for k in ("h2d_ms", "gate_ms", "fit_ms", "heavy_ms", "post_ms", "pack_ms", "d2h_ms",
-                                          "total_ms", "heavy_pre_ms", "fit_phase_ms")] + [("kernel_launches", C.c_int64), ("n_heavy", C.c_int64),
+                                          "total_ms", "heavy_pre_ms", "fit_phase_ms")] + [("kernel_launches", C.c_int64), ("n_heavy", C.c_int64), ("n_deferred", C.c_int64),
                                                             ("fast_seed", C.c_uint64), ("fast_lattice", C.c_uint64)]
 
 

@@ -17,6 +17,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <chrono>
 #include <string>
 #include <vector>
 
@@ -105,6 +106,7 @@ struct ns_ctx {
     cudaEvent_t ev[10];
     ns_timings tm;
     ns_counters *h_counters = nullptr; /* pinned */
+    int *h_started = nullptr, *d_started = nullptr; /* mapped pinned flag written by k_fit_heavy */
     int64_t chunk_units = 0;           /* 0 = auto */
 };
 
@@ -198,6 +200,8 @@ ns_ctx *ns_create(int device, char *err, size_t errlen)
     for (int i = 0; i < 10 && ok; i++)
         ok = cudaEventCreate(&ctx->ev[i]) == cudaSuccess;
     ok = ok && cudaMallocHost((void **)&ctx->h_counters, sizeof(ns_counters)) == cudaSuccess;
+    ok = ok && cudaHostAlloc((void **)&ctx->h_started, sizeof(int), cudaHostAllocMapped) == cudaSuccess &&
+         cudaHostGetDevicePointer((void **)&ctx->d_started, ctx->h_started, 0) == cudaSuccess;
     ok = ok && ctx->counters.reserve(1) == cudaSuccess;
     if (!ok) {
         if (err && errlen)
@@ -237,6 +241,8 @@ void ns_destroy(ns_ctx *ctx)
         cudaEventDestroy(ctx->ev[i]);
     if (ctx->h_counters)
         cudaFreeHost(ctx->h_counters);
+    if (ctx->h_started)
+        cudaFreeHost(ctx->h_started);
     cudaStreamDestroy(ctx->own_stream);
     cudaStreamDestroy(ctx->copy_stream);
     cudaStreamDestroy(ctx->heavy_stream);
@@ -389,7 +395,8 @@ static cudaError_t ns_reserve_units(ns_ctx *ctx, size_t U)
 
 /* cluster launch of k_fit_heavy: CL CTAs per unit, as many clusters as can be co-resident */
 static cudaError_t ns_launch_heavy(ns_ctx *ctx, cudaStream_t st, int n, int n_units_max, size_t smh, const ns_unit_src &src,
-                                   const ns_params &dprm, int64_t u0, const ns_unit_arrays &ua, int which)
+                                   const ns_params &dprm, int64_t u0, const ns_unit_arrays &ua, int which,
+                                   int *n_clusters_out)
 {
     const int wpc = NS_HEAVY_THREADS / 32;
     int cl = 1;
@@ -421,7 +428,10 @@ static cudaError_t ns_launch_heavy(ns_ctx *ctx, cudaStream_t st, int n, int n_un
         ncl = n_units_max;
     cfg.gridDim = dim3(cl * ncl);
     ns_counters *cp = ctx->counters.p;
-    return cudaLaunchKernelEx(&cfg, k_fit_heavy, src, dprm, u0, ua, cp, which);
+    int *started = which == 0 ? ctx->d_started : nullptr;
+    if (n_clusters_out)
+        *n_clusters_out = ncl;
+    return cudaLaunchKernelEx(&cfg, k_fit_heavy, src, dprm, u0, ua, cp, which, started);
 }
 
 static float ev_ms(cudaEvent_t a, cudaEvent_t b)
@@ -492,7 +502,19 @@ static int ns_run_chunk(ns_ctx *ctx, const ns_params &dprm, const double *qtab, 
         CK(cudaEventRecord(ctx->ev_fork, st));
         CK(cudaStreamWaitEvent(ctx->heavy_stream, ctx->ev_fork, 0));
         CK(cudaEventRecord(ctx->ev_h0, ctx->heavy_stream));
-        CK(ns_launch_heavy(ctx, ctx->heavy_stream, n, n_pre, smh, src, dprm, u0_src, ua, 0));
+        int ncl = 0;
+        *(volatile int *)ctx->h_started = 0;
+        CK(ns_launch_heavy(ctx, ctx->heavy_stream, n, n_pre, smh, src, dprm, u0_src, ua, 0, &ncl));
+        /* Let the clusters take their SMs before the persistent warp kernel fills the machine: a
+         * cluster needs whole SMs, the warp kernel's CTAs would never give them back.  Host-side
+         * wait on a mapped flag (bounded), not a kernel waiting on a kernel. */
+        if (n_light > 0) {
+            const auto t0 = std::chrono::steady_clock::now();
+            while (*(volatile int *)ctx->h_started < ncl) {
+                if (std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() > 0.02)
+                    break;
+            }
+        }
         CK(cudaEventRecord(ctx->ev_h1, ctx->heavy_stream));
         CK(cudaEventRecord(ctx->ev_join, ctx->heavy_stream));
         heavy_forked = true;
@@ -525,7 +547,7 @@ static int ns_run_chunk(ns_ctx *ctx, const ns_params &dprm, const double *qtab, 
         CK(cudaStreamWaitEvent(st, ctx->ev_join, 0));
     if (n_light > 0) {
         /* handed over by the warp kernel (count is on the device: a few CTAs that exit at once if none) */
-        CK(ns_launch_heavy(ctx, st, n, n_light < 64 ? n_light : 64, smh, src, dprm, u0_src, ua, 1));
+        CK(ns_launch_heavy(ctx, st, n, n_light < 64 ? n_light : 64, smh, src, dprm, u0_src, ua, 1, nullptr));
         ctx->tm.kernel_launches++;
     }
     CK(cudaEventRecord(ctx->ev[3], st));
@@ -627,6 +649,7 @@ static int ns_run_chunk(ns_ctx *ctx, const ns_params &dprm, const double *qtab, 
         ctx->tm.heavy_pre_ms += ev_ms(ctx->ev_h0, ctx->ev_h1);
     ctx->tm.fit_phase_ms += ev_ms(ctx->ev[2], ctx->ev[3]);
     ctx->tm.n_heavy += ctx->h_counters->n_heavy + ctx->h_counters->n_pre;
+    ctx->tm.n_deferred += ctx->h_counters->n_heavy;
     ctx->tm.fast_seed += ctx->h_counters->fast_seed;
     ctx->tm.fast_lattice += ctx->h_counters->fast_lattice;
     ctx->tm.post_ms += ev_ms(ctx->ev[3], ctx->ev[4]);

@@ -96,7 +96,7 @@ k_fit(ns_unit_src src, ns_params prm, int64_t u0, ns_unit_arrays ua, ns_counters
  * warp takes one sample at a time and its lanes share that sample's window (ns_coop.cuh); sums
  * over samples are exchanged through distributed shared memory (ClusterG). */
 __global__ void __launch_bounds__(NS_HEAVY_THREADS, 1)
-k_fit_heavy(ns_unit_src src, ns_params prm, int64_t u0, ns_unit_arrays ua, ns_counters *cnt, int which)
+k_fit_heavy(ns_unit_src src, ns_params prm, int64_t u0, ns_unit_arrays ua, ns_counters *cnt, int which, int *started)
 {
     const int n = src.n;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -122,6 +122,11 @@ k_fit_heavy(ns_unit_src src, ns_params prm, int64_t u0, ns_unit_arrays ua, ns_co
     int *next = which ? &cnt->next_heavy : &cnt->next_pre;
     const int *list = which ? ua.heavy_list : ua.pre_list;
     const unsigned crank = ClusterG::crank(), csize = ClusterG::csize();
+    /* tell the host that this cluster is resident (it then launches the warp kernel next to us) */
+    if (started && crank == 0 && threadIdx.x == 0) {
+        atomicAdd_system(started, 1);
+        __threadfence_system();
+    }
     __syncthreads();
     for (;;) {
         ClusterG::csync(); /* the previous unit is finished everywhere, s_idx may be overwritten */
