@@ -133,6 +133,8 @@ typedef struct ns_ctx ns_ctx;
 
 /* ---- life cycle ------------------------------------------------------------------ */
 int ns_abi_version(void);
+/* sizeof(ns_params), sizeof(ns_out), sizeof(ns_timings) for which = 0, 1, 2: lets a binding check its layout */
+size_t ns_sizeof(int which);
 /* one context per GPU and host thread; device = CUDA ordinal */
 ns_ctx *ns_create(int device, char *err, size_t errlen);
 void ns_destroy(ns_ctx *ctx);

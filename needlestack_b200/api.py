@@ -62,7 +62,7 @@ def load_library():
     return L
 
 
-EXPORTED_SYMBOLS = ("ns_abi_version", "ns_params_glm_default", "ns_params_caller_default", "ns_create", "ns_destroy",
+EXPORTED_SYMBOLS = ("ns_abi_version", "ns_sizeof", "ns_params_glm_default", "ns_params_caller_default", "ns_create", "ns_destroy",
                     "ns_last_error", "ns_set_stream", "ns_alloc_pinned", "ns_free_pinned", "ns_get_timings",
                     "ns_call_snv", "ns_call_snv_device", "ns_call_units", "ns_glmrob_nb", "ns_measure_fp64_peak")
 

@@ -125,6 +125,11 @@ extern "C" {
 
 int ns_abi_version(void) { return NS_ABI_VERSION; }
 
+size_t ns_sizeof(int which)
+{
+    return which == 0 ? sizeof(ns_params) : which == 1 ? sizeof(ns_out) : which == 2 ? sizeof(ns_timings) : 0;
+}
+
 void ns_params_glm_default(ns_params *p)
 { /* bin/glm_rob_nb.r:16-18 */
     memset(p, 0, sizeof(*p));
