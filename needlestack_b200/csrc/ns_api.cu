@@ -551,9 +551,14 @@ static int ns_run_chunk(ns_ctx *ctx, const ns_params &dprm, const double *qtab, 
     if (heavy_forked)
         CK(cudaStreamWaitEvent(st, ctx->ev_join, 0));
     if (n_light > 0) {
-        /* handed over by the warp kernel (count is on the device: a few CTAs that exit at once if none) */
-        CK(ns_launch_heavy(ctx, st, n, n_light < 64 ? n_light : 64, smh, src, dprm, u0_src, ua, 1, nullptr));
-        ctx->tm.kernel_launches++;
+        /* units the warp kernel handed over (rare): read their count, launch only if there are any */
+        CK(cudaMemcpyAsync(&ctx->h_counters->n_heavy, &ctx->counters.p->n_heavy, sizeof(int), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        const int n_def = ctx->h_counters->n_heavy;
+        if (n_def > 0) {
+            CK(ns_launch_heavy(ctx, st, n, n_def, smh, src, dprm, u0_src, ua, 1, nullptr));
+            ctx->tm.kernel_launches++;
+        }
     }
     CK(cudaEventRecord(ctx->ev[3], st));
     /* post */
@@ -674,9 +679,9 @@ static int64_t ns_pick_chunk(ns_ctx *ctx, int n, int64_t total_units)
     if (ctx->chunk_units > 0)
         return ctx->chunk_units;
     /* bound the per-chunk result planes (58 B per sample per row) to ~1.5 GB */
-    int64_t c = (int64_t)(1500.0e6 / (58.0 * n));
-    if (c > 3 * 131072)
-        c = 3 * 131072;
+    int64_t c = (int64_t)(6000.0e6 / (58.0 * n));
+    if (c > 3 * 262144)
+        c = 3 * 262144;
     if (c < 3 * 256)
         c = 3 * 256;
     c -= c % 3;

@@ -287,8 +287,16 @@ struct ns_fit_result {
 };
 
 /* sig.rob.tukey(sig) (glm_rob_nb.r:161-165), summed over the group's samples */
+#if defined(__CUDACC__)
+#define NS_GFN __host__ __device__ __noinline__
+#else
+#define NS_GFN
+#endif
+
+/* out of line on purpose: three call sites in the Brent driver; inlining them tripled the kernel's
+ * code and the warps stalled on instruction fetch (ncu: 32 % of issue stalls) */
 template <class G, int MODE>
-NS_GF inline double ns_sig_objective(double sig, const ns_work &w, int n, const ns_params &prm, ns_fit_counters &cnt,
+NS_GFN double ns_sig_objective(double sig, const ns_work &w, int n, const ns_params &prm, ns_fit_counters &cnt,
                                      int &need_heavy)
 {
     const double c = prm.c_tukey_sig;
@@ -497,7 +505,7 @@ NS_HD double ns_D_absmax(double u0, int ulen, double v0, int vlen)
 
 /* one IRLS pass (glm_rob_nb.r:188-200): returns the new beta, updates mu/eta */
 template <class G, int MODE>
-NS_GF inline double ns_irls_step(double sig, const ns_work &w, int n, double maxmu, const ns_params &prm,
+NS_GFN double ns_irls_step(double sig, const ns_work &w, int n, double maxmu, const ns_params &prm,
                                  ns_fit_result &res, int &need_heavy)
 {
     const int lane = G::lane();

@@ -12,7 +12,7 @@
 #define NS_COOP_DOUBLES (4 * NS_MAX_KNOTS)
 #define NS_RTAB_HEAVY 4096
 #ifndef NS_HEAVY_THREADS
-#define NS_HEAVY_THREADS 512 /* 16 warps = 16 samples of one unit in flight */
+#define NS_HEAVY_THREADS 512 /* 16 warps per CTA x 8 CTAs per cluster = one sample per warp at n <= 128 */
 #endif
 
 #define NS_WPB_GATE 8

@@ -1,0 +1,3 @@
+python bench.py --steps 3 --warmup 2 --no-cpu 2>/dev/null | python -c "
+import json,sys
+d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('full', round(d['value']), round(d['ms_per_step'],1), 'e2e', round(d['e2e']['value']), round(d['e2e']['ms_per_step'],1), {k:round(v,1) for k,v in d['detail']['kernel_ms_per_step_rank0'].items()}, 'frac', round(d['roofline']['frac'],3), d['detail']['heavy_units_per_step_rank0'], d['detail']['heavy_units_not_predicted_per_step_rank0'])"
