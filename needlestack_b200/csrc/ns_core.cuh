@@ -79,23 +79,23 @@ struct WarpG {
         double ex = __shfl_up_sync(0xffffffffu, inc, 1);
         return lane() == 0 ? -INFINITY : ex;
     }
-    /* tab[j] = sum_{k<j} 1/(a+k) = digamma(a+j) - digamma(a), j < J (J = 64) */
-    __device__ static __forceinline__ void fill_dtab(double *tab, double a, int J)
+    /* per-sigma tables, j < J (J = 64): tt[j] = 1/(a+j) (increments of digamma(a+j) - digamma(a)),
+     * r2[j] = (a+j)/(j+1) (pmf ratio without the mu/(mu+size) factor) */
+    __device__ static __forceinline__ void fill_dtab(double *tt, double *r2, const double *rt, double a, int J)
     {
         __syncwarp();
-        double carry = 0;
-        for (int base = 0; base < J; base += 32) {
-            double t = 1.0 / (a + (double)(base + lane()));
-            double inc = t;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                double u = __shfl_up_sync(0xffffffffu, inc, o);
-                if (lane() >= o)
-                    inc += u;
-            }
-            tab[base + lane()] = carry + (inc - t);
-            carry += __shfl_sync(0xffffffffu, inc, 31);
+        for (int j = lane(); j < J; j += 32) {
+            const double aj = a + (double)j;
+            r2[j] = aj * rt[j + 1];
+            tt[j] = 1.0 / aj;
         }
+        __syncwarp();
+    }
+    __device__ static __forceinline__ void fill_r2tab(double *r2, const double *rt, double a, int J)
+    {
+        __syncwarp();
+        for (int j = lane(); j < J; j += 32)
+            r2[j] = (a + (double)j) * rt[j + 1];
         __syncwarp();
     }
     /* replica-local variants (identical to the group-wide ones unless the group spans CTAs) */
@@ -145,7 +145,8 @@ struct CoopG {
     __device__ static __forceinline__ int isum(int v) { return (int)sum((double)v); }
     __device__ static __forceinline__ int any(int p) { return __syncthreads_or(p); }
     __device__ static __forceinline__ void sync() { __syncthreads(); }
-    __device__ static __forceinline__ void fill_dtab(double *, double, int) {}
+    __device__ static __forceinline__ void fill_dtab(double *, double *, const double *, double, int) {}
+    __device__ static __forceinline__ void fill_r2tab(double *, const double *, double, int) {}
     /* replica-local variants (identical to the group-wide ones unless the group spans CTAs) */
     __device__ static __forceinline__ int lnl() { return nl(); }
     __device__ static __forceinline__ int llane() { return lane(); }
@@ -234,7 +235,8 @@ struct ClusterG {
     __device__ static __forceinline__ double max(double v) { return allreduce<1>(v); }
     __device__ static __forceinline__ int isum(int v) { return (int)sum((double)v); }
     __device__ static __forceinline__ int any(int p) { return sum(__syncthreads_or(p) ? 1.0 : 0.0) > 0.0; }
-    __device__ static __forceinline__ void fill_dtab(double *, double, int) {}
+    __device__ static __forceinline__ void fill_dtab(double *, double *, const double *, double, int) {}
+    __device__ static __forceinline__ void fill_r2tab(double *, const double *, double, int) {}
 };
 
 /* one CTA = one unit (the heavy kernel): reductions through shared memory */
@@ -277,7 +279,8 @@ struct BlockG {
     __device__ static __forceinline__ int isum(int v) { return (int)sum((double)v); }
     __device__ static __forceinline__ int any(int p) { return __syncthreads_or(p); }
     __device__ static __forceinline__ void sync() { __syncthreads(); }
-    __device__ static __forceinline__ void fill_dtab(double *, double, int) {}
+    __device__ static __forceinline__ void fill_dtab(double *, double *, const double *, double, int) {}
+    __device__ static __forceinline__ void fill_r2tab(double *, const double *, double, int) {}
     /* replica-local variants (identical to the group-wide ones unless the group spans CTAs) */
     __device__ static __forceinline__ int lnl() { return nl(); }
     __device__ static __forceinline__ int llane() { return lane(); }
@@ -304,13 +307,17 @@ struct SerialG {
     static NS_HD double bcast(double v, int) { return v; }
     static NS_HD double excl_suffix_min(double) { return INFINITY; }
     static NS_HD double excl_prefix_max(double) { return -INFINITY; }
-    static NS_HD void fill_dtab(double *tab, double a, int J)
+    static NS_HD void fill_dtab(double *tt, double *r2, const double *rt, double a, int J)
     {
-        double acc = 0;
         for (int j = 0; j < J; j++) {
-            tab[j] = acc;
-            acc += 1.0 / (a + (double)j);
+            r2[j] = (a + (double)j) * rt[j + 1];
+            tt[j] = 1.0 / (a + (double)j);
         }
+    }
+    static NS_HD void fill_r2tab(double *r2, const double *rt, double a, int J)
+    {
+        for (int j = 0; j < J; j++)
+            r2[j] = (a + (double)j) * rt[j + 1];
     }
     /* replica-local variants (identical to the group-wide ones unless the group spans CTAs) */
     static NS_HD int lnl() { return nl(); }

@@ -261,11 +261,12 @@ static __device__ __noinline__ void ns_E12_coop(double mui, double sig, double c
 struct ns_work {
     double *y, *x, *X, *mu, *eta; /* n each; x <= 0 marks a sample that is not in the fit */
     double *scratch;              /* n + 8 */
-    double *dtab;                 /* NS_JTAB: digamma(j+1/sig) - digamma(1/sig) for the current sigma */
+    double *dtab;                 /* NS_JTAB: 1/(j+1/sig), the increments of digamma(j+1/sig) for the current sigma */
+    double *r2tab;                /* NS_JTAB: (j+1/sig)/(j+1) for the current sigma (pmf ratio without mu/(mu+size)) */
     const double *rtab;           /* NS_RTAB: 1/j (shared by the CTA) */
     ns_coop_scratch coop;         /* MODE 2 only: this warp's spline arrays */
 };
-NS_HD size_t ns_work_doubles(int n) { return (size_t)6 * (size_t)n + 8 + NS_JTAB; }
+NS_HD size_t ns_work_doubles(int n) { return (size_t)6 * (size_t)n + 8 + 2 * NS_JTAB; }
 NS_HD void ns_work_bind(ns_work &w, double *base, int n, const double *rtab)
 {
     w.y = base;
@@ -275,6 +276,7 @@ NS_HD void ns_work_bind(ns_work &w, double *base, int n, const double *rtab)
     w.eta = base + 4 * (size_t)n;
     w.scratch = base + 5 * (size_t)n;
     w.dtab = base + 6 * (size_t)n + 8;
+    w.r2tab = w.dtab + NS_JTAB;
     w.rtab = rtab;
 }
 
@@ -304,7 +306,7 @@ NS_GFN double ns_sig_objective(double sig, const ns_work &w, int n, const ns_par
     double acc = 0;
     int qerr = 0;
     if (MODE == 1) {
-        G::fill_dtab(w.dtab, invsig, NS_JTAB);
+        G::fill_dtab(w.dtab, w.r2tab, w.rtab, invsig, NS_JTAB);
         double dg0 = 0;
         bool have_dg0 = false;
         const double twon = (double)(2 * prm.n_ai_sig_tukey);
@@ -318,24 +320,26 @@ NS_GFN double ns_sig_objective(double sig, const ns_work &w, int n, const ns_par
             cnt.n_seed += 1;
             double term;
             if (j1 == 0 && j2 < (double)NS_JTAB) {
-                /* window {0..j2}: everything by recurrence, no division inside the loop */
+                /* window {0..j2}: everything by recurrence, no division inside the loop.
+                 * t_j = (j-mu)/(c sd) = t0 + j/(c sd);  psi_j = D_j - lg - (j-mu)/(mu+1/sig) = D_j + C0 - j/(mu+1/sig) */
                 const double lg = log(s1);
                 double pm = exp(-invsig * lg); /* dnbinom(0) = (1+sig*mu)^(-1/sig) */
                 const double inv_csd = 1.0 / (c * sd), inv_mpi = 1.0 / (mu + invsig);
                 const double q = mu * inv_mpi;
+                const double t0 = -mu * inv_csd, C0 = mu * inv_mpi - lg;
                 const int J2 = (int)j2;
                 const int yi = (y <= j2) ? (int)y : -1;
-                double a = 0, ty = 0;
+                double a = 0, ty = 0, jd = 0.0, D = C0; /* D = digamma(j+1/sig) - digamma(1/sig) + C0 */
                 for (int j = 0; j <= J2; j++) {
-                    const double d = (double)j - mu;
-                    const double t = d * inv_csd;
-                    double wt = t * t - 1;
+                    const double t = fma(jd, inv_csd, t0);
+                    double wt = fma(t, t, -1.0);
                     wt *= wt;
-                    const double wpsi = wt * (w.dtab[j] - lg - d * inv_mpi);
-                    a += wpsi * pm;
-                    if (j == yi)
-                        ty = wpsi; /* (psi_c(r)/r) * psi.sig.ML(r) at r = (y-mu)/sd */
-                    pm *= ((double)j + invsig) * w.rtab[j + 1] * q;
+                    const double wpsi = wt * fma(-jd, inv_mpi, D);
+                    a = fma(wpsi, pm, a);
+                    ty = (j == yi) ? wpsi : ty; /* (psi_c(r)/r) * psi.sig.ML(r) at r = (y-mu)/sd */
+                    pm *= w.r2tab[j] * q;
+                    D += w.dtab[j];
+                    jd += 1.0;
                 }
                 term = ty - a;
                 if (y == mu)
@@ -524,21 +528,23 @@ NS_GFN double ns_irls_step(double sig, const ns_work &w, int n, double maxmu, co
         if (MODE == 1) {
             const double j1 = fmax(ceil(mu - c * sV), 0.0), j2 = floor(mu + c * sV);
             res.cnt.n_seed += 1;
-            if (j1 == 0 && j2 < (double)(NS_RTAB - 1)) {
+            if (j1 == 0 && j2 < (double)NS_JTAB) {
                 double pm = exp(-invsig * log(sig * mu + 1));
                 const double inv_csd = 1.0 / (c * sV);
                 const double q = mu / (mu + invsig);
+                const double t0 = -mu * inv_csd;
                 const int J2 = (int)j2;
-                double a1 = 0, a2 = 0;
+                double a1 = 0, a2 = 0, jd = 0.0;
                 for (int j = 0; j <= J2; j++) {
-                    const double d = (double)j - mu;
-                    const double t = d * inv_csd;
-                    double wt = t * t - 1;
+                    const double t = fma(jd, inv_csd, t0);
+                    double wt = fma(t, t, -1.0);
                     wt *= wt;
-                    const double wp = wt * pm;
-                    a1 += wp * d;
-                    a2 += wp * (d * d);
-                    pm *= ((double)j + invsig) * w.rtab[j + 1] * q;
+                    const double d = jd - mu;
+                    const double wpd = (wt * pm) * d;
+                    a1 += wpd;
+                    a2 = fma(wpd, d, a2);
+                    pm *= w.r2tab[j] * q;
+                    jd += 1.0;
                 }
                 e1 = a1 / sV;
                 sap = a2 / sV;
@@ -741,6 +747,8 @@ NS_GF inline void ns_fit_unit(const ns_work &w, int n, double maxmu, const ns_pa
         double beta0 = beta1 + tol + 1;
         int len0 = 1;
         int it_mu = 0;
+        if (MODE == 1)
+            G::fill_r2tab(w.r2tab, w.rtab, 1 / sig, NS_JTAB); /* sigma is fixed over the IRLS passes */
         while (ns_D_absmax(beta1, len1, beta0, len0) > tol && it_mu < prm.maxit) {
             beta0 = beta1;
             len0 = len1;
