@@ -41,7 +41,7 @@ __device__ __forceinline__ void ns_store_fit(const ns_unit_arrays &ua, int u, ui
 
 /* persistent warps, one unit per warp at a time, fast (table/recurrence) path */
 #ifndef NS_FIT_MINB
-#define NS_FIT_MINB 4
+#define NS_FIT_MINB 5
 #endif
 __global__ void __launch_bounds__(128, NS_FIT_MINB)
 k_fit(ns_unit_src src, ns_params prm, int64_t u0, ns_unit_arrays ua, ns_counters *cnt)

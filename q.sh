@@ -1,3 +1,5 @@
-python bench.py --steps 3 --warmup 2 --positions 200000 --no-cpu --no-e2e --p-germline 0 2>/dev/null | python -c "
+make -s -C oracle
+python -m pytest tests -q -m gpu -x 2>&1 | tail -4
+python bench.py --steps 3 --warmup 2 --positions 200000 --no-cpu --no-e2e 2>/dev/null | python -c "
 import json,sys
-d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('nogerm', round(d['value']), round(d['ms_per_step'],1), {k:round(v,1) for k,v in d['detail']['kernel_ms_per_step_rank0'].items()}, 'frac', round(d['roofline']['frac'],3))"
+d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('germ', round(d['value']), round(d['ms_per_step'],1), {k:round(v,1) for k,v in d['detail']['kernel_ms_per_step_rank0'].items()}, 'frac', round(d['roofline']['frac'],3), 'gate', round(d['roofline_gate']['achieved']), d['detail']['heavy_units_per_step_rank0'], d['detail']['heavy_units_not_predicted_per_step_rank0'])"
