@@ -145,7 +145,11 @@ def _ptr(a):
 class Caller:
     """One GPU context (ns_ctx).  Not thread-safe; one per device and host thread."""
 
-    def __init__(self, device=0):
+    def __init__(self, device=0, reuse_outputs=False):
+        """reuse_outputs=True: results are views into page-locked buffers owned by the Caller and are
+        overwritten by its next call (fast D2H, no per-call allocation); False: fresh numpy arrays."""
+        self._reuse = bool(reuse_outputs)
+        self._pool = {}
         self._L = load_library()
         err = C.create_string_buffer(512)
         self._ctx = self._L.ns_create(int(device), err, 512)
@@ -157,6 +161,25 @@ class Caller:
         if getattr(self, "_ctx", None):
             self._L.ns_destroy(self._ctx)
             self._ctx = None
+        for pa in getattr(self, "_pool", {}).values():
+            pa.free()
+        self._pool = {}
+
+    def _buf(self, name, shape, dtype, fill=None):
+        """output array: pinned and pooled when reuse_outputs, else a fresh numpy array"""
+        if not self._reuse:
+            return np.empty(shape, dtype=dtype) if fill is None else np.full(shape, fill, dtype=dtype)
+        need = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        pa = self._pool.get(name)
+        if pa is None or pa.nbytes < need:
+            if pa is not None:
+                pa.free()
+            pa = PinnedArray((max(need + need // 4, 64),), np.uint8)
+            self._pool[name] = pa
+        arr = pa.array[:need].view(dtype).reshape(shape)
+        if fill is not None:
+            arr[...] = fill
+        return arr
 
     def __del__(self):
         try:
@@ -189,28 +212,29 @@ class Caller:
         return v.value
 
     # -- output allocation ---------------------------------------------------------------
-    @staticmethod
-    def _alloc_out(U, n, emit_cap, want_rows=True):
+    def _alloc_out(self, U, n, emit_cap, want_rows=True):
         o = NsOut()
-        a = dict(sigma=np.empty(U), slope=np.empty(U), max_gq=np.empty(U), flags=np.zeros(U, dtype=np.uint32),
-                 iters=np.zeros(U, dtype=np.uint32), emit_index=np.full(U, -1, dtype=np.int32),
-                 unit_cycles=np.zeros(U, dtype=np.uint64))
-        o.unit_cycles = a["unit_cycles"].ctypes.data_as(C.POINTER(C.c_uint64))
+        B = self._buf
+        a = dict(sigma=B("sigma", (U,), np.float64), slope=B("slope", (U,), np.float64),
+                 max_gq=B("max_gq", (U,), np.float64), flags=B("flags", (U,), np.uint32),
+                 iters=B("iters", (U,), np.uint32), emit_index=B("emit_index", (U,), np.int32),
+                 unit_cycles=B("unit_cycles", (U,), np.uint64))
         o.sigma, o.slope, o.max_gq = (a[k].ctypes.data_as(c_dp) for k in ("sigma", "slope", "max_gq"))
         o.flags = a["flags"].ctypes.data_as(c_up)
         o.iters = a["iters"].ctypes.data_as(c_up)
         o.emit_index = a["emit_index"].ctypes.data_as(c_ip)
+        o.unit_cycles = a["unit_cycles"].ctypes.data_as(C.POINTER(C.c_uint64))
         o.emit_cap = emit_cap if want_rows else 0
         if want_rows:
             for k in ("pvalue", "qvalue", "gq", "qval_minaf", "sor", "rvsb", "fs"):
-                a[k] = np.empty((emit_cap, n))
+                a[k] = B(k, (emit_cap, n), np.float64)
                 setattr(o, k, a[k].ctypes.data_as(c_dp))
             for k in ("gt", "status"):
-                a[k] = np.zeros((emit_cap, n), dtype=np.uint8)
+                a[k] = B(k, (emit_cap, n), np.uint8)
                 setattr(o, k, a[k].ctypes.data_as(c_bp))
-            a["pooled"] = np.empty((emit_cap, 8))
+            a["pooled"] = B("pooled", (emit_cap, 8), np.float64)
             o.pooled = a["pooled"].ctypes.data_as(c_dp)
-            a["emit_unit"] = np.empty(emit_cap, dtype=np.int64)
+            a["emit_unit"] = B("emit_unit", (emit_cap,), np.int64)
             o.emit_unit = a["emit_unit"].ctypes.data_as(c_lp)
         return o, a
 

@@ -50,7 +50,7 @@ __device__ __forceinline__ void ns_gate_commit(const ns_unit_arrays &ua, ns_coun
          * straight to the cluster-per-unit kernel, which runs next to the warp kernel on its own
          * stream.  Over-prediction only costs efficiency. */
         const double kwin = mu_hint * (1.0 + prm.c_tukey_sig * sqrt(prm.maxsig + 1.0 / fmax(mu_hint, 1e-300)));
-        if (kwin > 2.0 * prm.n_ai_sig_tukey)
+        if (kwin > 1.0 * prm.n_ai_sig_tukey) /* half the switch point: the slope usually grows from its first estimate */
             ua.pre_list[atomicAdd(&cnt->n_pre, 1)] = u;
         else
             ua.fit_list[atomicAdd(&cnt->n_light, 1)] = u;
