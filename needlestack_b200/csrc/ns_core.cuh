@@ -87,7 +87,7 @@ struct WarpG {
         for (int j = lane(); j < J; j += 32) {
             const double aj = a + (double)j;
             r2[j] = aj * rt[j + 1];
-            tt[j] = 1.0 / aj;
+            tt[j] = ns_frcp(aj);
         }
         __syncwarp();
     }

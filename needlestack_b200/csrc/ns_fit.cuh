@@ -315,7 +315,7 @@ NS_GFN double ns_sig_objective(double sig, const ns_work &w, int n, const ns_par
                 continue;
             const double mu = w.mu[i], y = w.y[i];
             const double s1 = sig * mu + 1;
-            const double sd = sqrt(mu * s1);
+            const double sd = ns_fsqrt(mu * s1);
             const double j1 = fmax(ceil(mu - c * sd), 0.0), j2 = floor(mu + c * sd);
             cnt.n_seed += 1;
             double term;
@@ -324,7 +324,7 @@ NS_GFN double ns_sig_objective(double sig, const ns_work &w, int n, const ns_par
                  * t_j = (j-mu)/(c sd) = t0 + j/(c sd);  psi_j = D_j - lg - (j-mu)/(mu+1/sig) = D_j + C0 - j/(mu+1/sig) */
                 const double lg = log(s1);
                 double pm = exp(-invsig * lg); /* dnbinom(0) = (1+sig*mu)^(-1/sig) */
-                const double inv_csd = 1.0 / (c * sd), inv_mpi = 1.0 / (mu + invsig);
+                const double inv_csd = ns_frcp(c * sd), inv_mpi = ns_frcp(mu + invsig);
                 const double q = mu * inv_mpi;
                 const double t0 = -mu * inv_csd, C0 = mu * inv_mpi - lg;
                 const int J2 = (int)j2;
@@ -524,14 +524,14 @@ NS_GFN double ns_irls_step(double sig, const ns_work &w, int n, double maxmu, co
         const double mu = w.mu[i], eta = w.eta[i], y = w.y[i];
         double e1, sap;
         const double V = ns_varfunc(mu, sig);
-        const double sV = sqrt(V);
+        const double sV = (MODE == 1) ? ns_fsqrt(V) : sqrt(V);
         if (MODE == 1) {
             const double j1 = fmax(ceil(mu - c * sV), 0.0), j2 = floor(mu + c * sV);
             res.cnt.n_seed += 1;
             if (j1 == 0 && j2 < (double)NS_JTAB) {
                 double pm = exp(-invsig * log(sig * mu + 1));
-                const double inv_csd = 1.0 / (c * sV);
-                const double q = mu / (mu + invsig);
+                const double inv_csd = ns_frcp(c * sV);
+                const double q = mu * ns_frcp(mu + invsig);
                 const double t0 = -mu * inv_csd;
                 const int J2 = (int)j2;
                 double a1 = 0, a2 = 0, jd = 0.0;
@@ -546,8 +546,9 @@ NS_GFN double ns_irls_step(double sig, const ns_work &w, int n, double maxmu, co
                     pm *= w.r2tab[j] * q;
                     jd += 1.0;
                 }
-                e1 = a1 / sV;
-                sap = a2 / sV;
+                const double isV = ns_frcp(sV);
+                e1 = a1 * isV;
+                sap = a2 * isV;
                 res.cnt.n_lattice += (unsigned long long)(J2 + 1);
             } else if (j1 > j2) {
                 e1 = 0;
@@ -568,8 +569,14 @@ NS_GFN double ns_irls_step(double sig, const ns_work &w, int n, double maxmu, co
                 ns_E_tukeypsi_12(mu, sig, c, prm.n_ai_sig_tukey, res.cnt, e1, sap);
         }
         double ee = (MODE == 1) ? mu : exp(eta); /* derivinvlink(eta) = exp(log(mu)) */
-        double bi = sap * (1.0 / (V * sV)) * (ee * ee);
-        double ei = (ns_tukeypsi((y - mu) / sV, c) - e1) / sap * V * (1 / mu);
+        double bi, ei;
+        if (MODE == 1) {
+            bi = sap * ns_frcp(V * sV) * (ee * ee);
+            ei = (ns_tukeypsi((y - mu) * ns_frcp(sV), c) - e1) * ns_frcp(sap) * V * ns_frcp(mu);
+        } else {
+            bi = sap * (1.0 / (V * sV)) * (ee * ee);
+            ei = (ns_tukeypsi((y - mu) / sV, c) - e1) / sap * V * (1 / mu);
+        }
         double zi = eta + ei;
         if (bi != bi || zi != zi) {
             nanrows++; /* lm(): na.omit drops the row */

@@ -30,6 +30,39 @@
 #define NS_DBL_MIN 2.2250738585072014e-308
 #define NS_DBL_MAX 1.7976931348623157e+308
 
+/* Branch-free reciprocal and square root for operands that are known to be normal and positive
+ * (variances, means, window widths): hardware seed (MUFU.RCP64H / RSQ64H, ~20 bits) and two
+ * Newton steps, <= 1-2 ulp.  The IEEE-exact `/` and sqrt() cost ~3x as many instructions because of
+ * their special-case paths (ncu: 25 % of k_fit's instructions were division sequences).  On the
+ * host (emulation build) they are the plain operations. */
+#if defined(__CUDA_ARCH__)
+__device__ __forceinline__ double ns_frcp(double a)
+{
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(a));
+    double e = fma(-a, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-a, r, 1.0);
+    r = fma(r, e, r);
+    return r;
+}
+__device__ __forceinline__ double ns_fsqrt(double a)
+{
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));
+    /* y ~ 1/sqrt(a): two Newton steps on y, then s = a*y with one correction */
+    double h = 0.5 * a;
+    y = y * fma(-h * y, y, 1.5);
+    y = y * fma(-h * y, y, 1.5);
+    double s = a * y;
+    s = fma(fma(-s, s, a), 0.5 * y, s);
+    return (a > 0.0) ? s : ((a == 0.0) ? 0.0 : NAN);
+}
+#else
+static inline double ns_frcp(double a) { return 1.0 / a; }
+static inline double ns_fsqrt(double a) { return sqrt(a); }
+#endif
+
 /* ---- constant tables: __constant__ on the device, plain statics on the host ---- */
 #define NS_SFERR_INIT                                                                              \
     {0.0, 0.1534264097200273452913839, 0.08106146679532725821967026,                               \
