@@ -176,6 +176,35 @@ int ns_glmrob_nb(ns_ctx *ctx, const ns_params *prm, int n_samples, const int32_t
                  const int32_t *x, double *sigma, double *slope, double *pvalues, double *qvalues,
                  double *gq, int32_t *extra_rob, uint32_t *flags);
 
+/* ---- columnar loader for the mpileup2readcounts text table ------------------------------------
+ * Replaces the per-line strsplit / column gathers of bin/needlestack.r:316-329 (SNV), :461-479 (DEL),
+ * :624-643 (INS).  Host code, multi-threaded; the count planes are page-locked when a CUDA device is
+ * present so they can go straight into ns_call_snv.  The table owns everything it returns. */
+typedef struct ns_table ns_table;
+/* text: the whole table (3 + 11 n tab-separated columns per line; chr, loc, ref, then per sample
+ * depth,A,T,C,G,a,t,c,g,INS,DEL); has_header != 0 skips the first line (bin/needlestack.r:317). */
+ns_table *ns_table_parse(const char *text, size_t len, int n_samples, int has_header, int n_threads, char *err,
+                         size_t errlen);
+void ns_table_free(ns_table *t);
+int64_t ns_table_positions(const ns_table *t);
+int ns_table_samples(const ns_table *t);
+int ns_table_counts_pinned(const ns_table *t);
+const int32_t *ns_table_counts(const ns_table *t);  /* [P][9][n], the `counts` argument of ns_call_snv */
+const uint8_t *ns_table_ref(const ns_table *t);     /* [P] 0..3 = A,T,C,G, 4 = skipped (bin/needlestack.r:319) */
+const char *ns_table_ref_text(const ns_table *t);   /* [P] first character of the REF column as written */
+const int64_t *ns_table_loc(const ns_table *t);     /* [P] column 2 */
+const int32_t *ns_table_chrom(const ns_table *t);   /* [P] index into the chromosome dictionary */
+int ns_table_n_chrom(const ns_table *t);
+const char *ns_table_chrom_name(const ns_table *t, int id);
+const int64_t *ns_table_indel_cov(const ns_table *t); /* [P][2] sum of all deletion / insertion counts */
+/* indel units: one per (position, unique upper-cased sequence), deletions before insertions per line */
+int64_t ns_table_indel_units(const ns_table *t);
+const int64_t *ns_table_indel_pos(const ns_table *t);  /* [Ui] row of the position */
+const uint8_t *ns_table_indel_type(const ns_table *t); /* [Ui] 1 = deletion, 2 = insertion */
+const char *ns_table_indel_seq(const ns_table *t, int64_t u);
+const int32_t *ns_table_indel_vp(const ns_table *t);   /* [Ui][n] forward-strand counts */
+const int32_t *ns_table_indel_vm(const ns_table *t);   /* [Ui][n] reverse-strand counts */
+
 /* FP64 FMA peak of the context's device, TFLOP/s (the denominator of the fit roofline) */
 int ns_measure_fp64_peak(ns_ctx *ctx, double *tflops);
 

@@ -56,6 +56,24 @@ def load_library():
                                 C.POINTER(NsOut)]
     L.ns_glmrob_nb.argtypes = [vp, C.POINTER(NsParams), C.c_int, vp, vp, c_dp, c_dp, c_dp, c_dp, c_dp, c_ip, c_up]
     L.ns_measure_fp64_peak.argtypes = [vp, c_dp]
+    L.ns_table_parse.restype = vp
+    L.ns_table_parse.argtypes = [C.c_char_p, C.c_size_t, C.c_int, C.c_int, C.c_int, C.c_char_p, C.c_size_t]
+    L.ns_table_free.argtypes = [vp]
+    L.ns_table_positions.restype = C.c_int64
+    L.ns_table_indel_units.restype = C.c_int64
+    for name in ("ns_table_positions", "ns_table_samples", "ns_table_counts_pinned", "ns_table_counts",
+                 "ns_table_ref", "ns_table_ref_text", "ns_table_loc", "ns_table_chrom", "ns_table_n_chrom",
+                 "ns_table_indel_cov", "ns_table_indel_units", "ns_table_indel_pos", "ns_table_indel_type",
+                 "ns_table_indel_vp", "ns_table_indel_vm"):
+        getattr(L, name).argtypes = [vp]
+    for name in ("ns_table_counts", "ns_table_ref", "ns_table_ref_text", "ns_table_loc", "ns_table_chrom",
+                 "ns_table_indel_cov", "ns_table_indel_pos", "ns_table_indel_type", "ns_table_indel_vp",
+                 "ns_table_indel_vm"):
+        getattr(L, name).restype = vp
+    L.ns_table_chrom_name.restype = C.c_char_p
+    L.ns_table_chrom_name.argtypes = [vp, C.c_int]
+    L.ns_table_indel_seq.restype = C.c_char_p
+    L.ns_table_indel_seq.argtypes = [vp, C.c_int64]
     if L.ns_abi_version() != _abi.NS_ABI_VERSION:
         raise NeedlestackError("libns_b200.so ABI version mismatch")
     _LIB = L
@@ -64,7 +82,12 @@ def load_library():
 
 EXPORTED_SYMBOLS = ("ns_abi_version", "ns_sizeof", "ns_params_glm_default", "ns_params_caller_default", "ns_create", "ns_destroy",
                     "ns_last_error", "ns_set_stream", "ns_alloc_pinned", "ns_free_pinned", "ns_get_timings",
-                    "ns_call_snv", "ns_call_snv_device", "ns_call_units", "ns_glmrob_nb", "ns_measure_fp64_peak")
+                    "ns_call_snv", "ns_call_snv_device", "ns_call_units", "ns_glmrob_nb", "ns_measure_fp64_peak",
+                    "ns_table_parse", "ns_table_free", "ns_table_positions", "ns_table_samples",
+                    "ns_table_counts_pinned", "ns_table_counts", "ns_table_ref", "ns_table_ref_text", "ns_table_loc",
+                    "ns_table_chrom", "ns_table_n_chrom", "ns_table_chrom_name", "ns_table_indel_cov",
+                    "ns_table_indel_units", "ns_table_indel_pos", "ns_table_indel_type", "ns_table_indel_seq",
+                    "ns_table_indel_vp", "ns_table_indel_vm")
 
 
 def make_params(pairs=None, defaults="caller", **kw):

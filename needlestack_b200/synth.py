@@ -116,7 +116,31 @@ def tn_pairs(cfg: Config):
                 only_t=np.empty(0, dtype=np.int32), only_n=np.empty(0, dtype=np.int32))
 
 
-def write_table(path, ref, counts, chrom="chr1", start=1, names=None):
+def random_indel_cells(P, n, seed=0, p_site=0.02):
+    """INS / DEL cells for write_table: dict (p, s) -> (ins_cell, del_cell) in the mpileup2readcounts
+    spelling 'count:SEQ|count:seq' (upper case = forward strand, lower case = reverse)"""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    cells = {}
+    for p in np.where(rng.random(P) < p_site)[0]:
+        pool = ["".join(rng.choice(list("ACGT"), size=rng.integers(1, 5))) for _ in range(rng.integers(1, 4))]
+        carriers = np.where(rng.random(n) < rng.choice([0.1, 0.5, 0.9]))[0]
+        for s in carriers:
+            out = []
+            for _ in range(2):
+                ent = []
+                for sq in pool:
+                    if rng.random() < 0.6:
+                        if rng.random() < 0.8:
+                            ent.append(f"{rng.integers(1, 40)}:{sq}")
+                        if rng.random() < 0.8:
+                            ent.append(f"{rng.integers(1, 40)}:{sq.lower()}")
+                rng.shuffle(ent)
+                out.append("|".join(ent) if ent else "NA")
+            cells[(int(p), int(s))] = tuple(out)
+    return cells
+
+
+def write_table(path, ref, counts, chrom="chr1", start=1, names=None, indel_cells=None):
     """Write a real mpileup2readcounts TEXT table (3 + 11 n tab-separated columns, header line,
     indel cells NA) so the reference driver could consume it."""
     P, _, n = counts.shape
@@ -130,5 +154,6 @@ def write_table(path, ref, counts, chrom="chr1", start=1, names=None):
             cells = [chrom, str(start + p), BASES[ref[p]] if ref[p] < 4 else "N"]
             row = counts[p]
             for i in range(n):
-                cells += [str(int(row[j, i])) for j in range(9)] + ["NA", "NA"]
+                ins, dele = (indel_cells or {}).get((p, i), ("NA", "NA"))
+                cells += [str(int(row[j, i])) for j in range(9)] + [ins, dele]
             f.write("\t".join(cells) + "\n")
