@@ -398,21 +398,45 @@ static cudaError_t ns_reserve_units(ns_ctx *ctx, size_t U)
     return ctx->cub_tmp.reserve(tmp + 256);
 }
 
+/* geometry of the cluster-per-unit kernel: threads per CTA and CTAs per cluster */
+static void ns_heavy_geometry(int n, int *threads, int *cl)
+{
+    int th = NS_HEAVY_THREADS;
+    const char *eth = getenv("NS_HEAVY_THREADS");
+    if (eth && (atoi(eth) == 128 || atoi(eth) == 256 || atoi(eth) == 512))
+        th = atoi(eth);
+    const int wpc = th / 32;
+    int c = 1;
+    while (c < 8 && c * wpc < n)
+        c <<= 1; /* enough warps for one sample per warp, up to the portable cluster size 8 */
+    const char *ecl = getenv("NS_HEAVY_CLUSTER");
+    if (ecl && atoi(ecl) >= 1 && atoi(ecl) <= 16)
+        c = atoi(ecl);
+    *threads = th;
+    *cl = c;
+}
+
+static size_t ns_heavy_smem(int n, int threads)
+{
+    return (NS_RTAB_HEAVY + ns_work_doubles(n) + (size_t)(threads / 32) * NS_COOP_DOUBLES) * sizeof(double);
+}
+
 /* cluster launch of k_fit_heavy: CL CTAs per unit, as many clusters as can be co-resident */
-static cudaError_t ns_launch_heavy(ns_ctx *ctx, cudaStream_t st, int n, int n_units_max, size_t smh, const ns_unit_src &src,
+static cudaError_t ns_launch_heavy(ns_ctx *ctx, cudaStream_t st, int n, int n_units_max, const ns_unit_src &src,
                                    const ns_params &dprm, int64_t u0, const ns_unit_arrays &ua, int which,
                                    int *n_clusters_out)
 {
-    const int wpc = NS_HEAVY_THREADS / 32;
-    int cl = 1;
-    while (cl < 8 && cl * wpc < n)
-        cl <<= 1; /* enough warps for one sample per warp, up to the portable cluster size 8 */
-    const char *ecl = getenv("NS_HEAVY_CLUSTER");
-    if (ecl && atoi(ecl) >= 1 && atoi(ecl) <= 8)
-        cl = atoi(ecl);
+    int threads, cl;
+    ns_heavy_geometry(n, &threads, &cl);
+    const size_t smh = ns_heavy_smem(n, threads);
+    cudaError_t e;
+    if (smh > 48 * 1024 && (e = cudaFuncSetAttribute(k_fit_heavy, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smh)))
+        return e;
+    if (cl > 8 && (e = cudaFuncSetAttribute(k_fit_heavy, cudaFuncAttributeNonPortableClusterSizeAllowed, 1)))
+        return e;
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
-    cfg.blockDim = dim3(NS_HEAVY_THREADS);
+    cfg.blockDim = dim3(threads);
     cfg.dynamicSmemBytes = smh;
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
@@ -424,7 +448,7 @@ static cudaError_t ns_launch_heavy(ns_ctx *ctx, cudaStream_t st, int n, int n_un
     cfg.numAttrs = 1;
     cfg.gridDim = dim3(cl);
     int ncl = 0;
-    cudaError_t e = cudaOccupancyMaxActiveClusters(&ncl, k_fit_heavy, &cfg);
+    e = cudaOccupancyMaxActiveClusters(&ncl, k_fit_heavy, &cfg);
     if (e != cudaSuccess)
         return e;
     if (ncl < 1)
@@ -491,17 +515,15 @@ static int ns_run_chunk(ns_ctx *ctx, const ns_params &dprm, const double *qtab, 
     /* fit: the CTA-per-unit kernel for the units predicted heavy runs on its own stream next to
      * the persistent warp kernel; units the warp kernel hands over later get a second pass */
     const int n_pre = ctx->h_counters->n_pre, n_light = ctx->h_counters->n_light;
-    const int hthreads = NS_HEAVY_THREADS;
-    const size_t smh = (NS_RTAB_HEAVY + ns_work_doubles(n) + (size_t)(hthreads / 32) * NS_COOP_DOUBLES) * sizeof(double);
     CK(cudaEventRecord(ctx->ev[2], st));
     bool heavy_forked = false;
     if (n_fit > 0) {
-        if (smh > 227 * 1024) {
+        int hth, hcl;
+        ns_heavy_geometry(n, &hth, &hcl);
+        if (ns_heavy_smem(n, hth) > 227 * 1024) {
             ctx->err = "too many samples for the heavy kernel's working set";
             return NS_ERR_ARG;
         }
-        if (smh > 48 * 1024)
-            CK(cudaFuncSetAttribute(k_fit_heavy, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smh));
     }
     if (n_pre > 0) {
         CK(cudaEventRecord(ctx->ev_fork, st));
@@ -509,7 +531,7 @@ static int ns_run_chunk(ns_ctx *ctx, const ns_params &dprm, const double *qtab, 
         CK(cudaEventRecord(ctx->ev_h0, ctx->heavy_stream));
         int ncl = 0;
         *(volatile int *)ctx->h_started = 0;
-        CK(ns_launch_heavy(ctx, ctx->heavy_stream, n, n_pre, smh, src, dprm, u0_src, ua, 0, &ncl));
+        CK(ns_launch_heavy(ctx, ctx->heavy_stream, n, n_pre, src, dprm, u0_src, ua, 0, &ncl));
         /* Let the clusters take their SMs before the persistent warp kernel fills the machine: a
          * cluster needs whole SMs, the warp kernel's CTAs would never give them back.  Host-side
          * wait on a mapped flag (bounded), not a kernel waiting on a kernel. */
@@ -556,7 +578,7 @@ static int ns_run_chunk(ns_ctx *ctx, const ns_params &dprm, const double *qtab, 
         CK(cudaStreamSynchronize(st));
         const int n_def = ctx->h_counters->n_heavy;
         if (n_def > 0) {
-            CK(ns_launch_heavy(ctx, st, n, n_def, smh, src, dprm, u0_src, ua, 1, nullptr));
+            CK(ns_launch_heavy(ctx, st, n, n_def, src, dprm, u0_src, ua, 1, nullptr));
             ctx->tm.kernel_launches++;
         }
     }

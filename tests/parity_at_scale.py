@@ -1,0 +1,59 @@
+"""Larger parity sweep (manual: `python tests/parity_at_scale.py [out.json]` on a GPU box): the CUDA path against
+the CPU oracle on every BASELINE shape at sizes the oracle finishes in about a minute each.  Writes one JSON
+report (profiles/parity_r1.json)."""
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+sys.path.insert(0, os.path.dirname(HERE))
+import orc  # noqa: E402
+import parity  # noqa: E402
+import needlestack_b200 as ns  # noqa: E402
+from needlestack_b200 import synth  # noqa: E402
+
+CASES = [("C1", 40000, {}, False), ("C2", 16000, {}, False), ("C2", 4000, {"extra_rob": 1}, False),
+         ("C3", 48, {}, False), ("C4", 1500, {}, True), ("C5", 300000, {}, False)]
+
+
+def main(out_path):
+    rep_all = []
+    threads = os.cpu_count() or 1
+    with ns.Caller(0) as c:
+        for cfgname, P, kw, tn in CASES:
+            cfg = synth.CONFIGS[cfgname]
+            ref, counts = synth.generate(cfg, P=P, seed=cfg.seed + 7)
+            pairs = synth.tn_pairs(cfg) if tn else None
+            t = time.time()
+            O = orc.call_snv_batch(ref, np.ascontiguousarray(counts.transpose(1, 0, 2)),
+                                   orc.call_params(pairs=pairs, **kw), n_threads=threads)
+            t_or = time.time() - t
+            t = time.time()
+            R = c.call_snv(ref, counts, prm=ns.make_params(pairs=pairs, emit_mode=ns.NS_EMIT_ALL, **kw))
+            t_gpu = time.time() - t
+            d = {k: R.dense(k) for k in ("pvalue", "qvalue", "gq", "qval_minaf", "sor", "rvsb", "fs", "pooled")}
+            d["gt"] = R.dense("gt", fill=0)
+            d["status"] = R.dense("status", fill=0)
+            for k in ("sigma", "slope", "max_gq", "flags", "n_outer"):
+                d[k] = R[k]
+            try:
+                rep = parity.compare(O, d, label=cfgname)
+                rep["ok"] = True
+            except AssertionError as e:
+                rep = dict(ok=False, error=str(e)[:2000])
+            rep.pop("bad", None)
+            rep.update(config=cfgname, positions=P, params=kw, tn_pairs=tn, oracle_seconds=round(t_or, 2),
+                       oracle_threads=threads, gpu_seconds=round(t_gpu, 3), calls=int(O["gate2"].sum()),
+                       heavy_units=int(c.timings()["n_heavy"]))
+            rep = {k: (float(v) if isinstance(v, (np.floating,)) else v) for k, v in rep.items()}
+            print(json.dumps(rep))
+            rep_all.append(rep)
+    json.dump(rep_all, open(out_path, "w"), indent=1)
+
+
+if __name__ == "__main__":
+    main(sys.argv[1] if len(sys.argv) > 1 else "parity_report.json")
