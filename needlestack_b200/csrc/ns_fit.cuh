@@ -322,8 +322,8 @@ NS_GFN double ns_sig_objective(double sig, const ns_work &w, int n, const ns_par
             if (j1 == 0 && j2 < (double)NS_JTAB) {
                 /* window {0..j2}: everything by recurrence, no division inside the loop.
                  * t_j = (j-mu)/(c sd) = t0 + j/(c sd);  psi_j = D_j - lg - (j-mu)/(mu+1/sig) = D_j + C0 - j/(mu+1/sig) */
-                const double lg = log(s1);
-                double pm = exp(-invsig * lg); /* dnbinom(0) = (1+sig*mu)^(-1/sig) */
+                const double lg = ns_flog(s1);
+                double pm = ns_fexp(-invsig * lg); /* dnbinom(0) = (1+sig*mu)^(-1/sig) */
                 const double inv_csd = ns_frcp(c * sd), inv_mpi = ns_frcp(mu + invsig);
                 const double q = mu * inv_mpi;
                 const double t0 = -mu * inv_csd, C0 = mu * inv_mpi - lg;
@@ -529,7 +529,7 @@ NS_GFN double ns_irls_step(double sig, const ns_work &w, int n, double maxmu, co
             const double j1 = fmax(ceil(mu - c * sV), 0.0), j2 = floor(mu + c * sV);
             res.cnt.n_seed += 1;
             if (j1 == 0 && j2 < (double)NS_JTAB) {
-                double pm = exp(-invsig * log(sig * mu + 1));
+                double pm = ns_fexp(-invsig * ns_flog(sig * mu + 1));
                 const double inv_csd = ns_frcp(c * sV);
                 const double q = mu * ns_frcp(mu + invsig);
                 const double t0 = -mu * inv_csd;
@@ -596,13 +596,13 @@ NS_GFN double ns_irls_step(double sig, const ns_work &w, int n, double maxmu, co
     for (int i = G::llane(); i < n; i += G::lnl()) { /* every replica updates all samples */
         if (!(w.x[i] > 0))
             continue;
-        double mu = exp(w.X[i] + beta);
+        double mu = (MODE == 1) ? ns_fexp(w.X[i] + beta) : exp(w.X[i] + beta);
         if (mu > maxmu)
             mu = maxmu;
         if (mu == 0)
             mu = prm.minmu;
         w.mu[i] = mu;
-        w.eta[i] = log(mu);
+        w.eta[i] = (MODE == 1) ? ns_flog(mu) : log(mu);
     }
     G::lsync();
     return beta;

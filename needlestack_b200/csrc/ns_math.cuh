@@ -15,6 +15,7 @@
 #include <math.h>
 #include <float.h>
 #include <stdint.h>
+#include <string.h>
 
 #if defined(__CUDACC__)
 #define NS_HD __host__ __device__ __forceinline__
@@ -114,6 +115,74 @@ static const double ns_h_wg[5] = NS_WG_INIT;
 #else
 #define NS_TBL(name) ns_h_##name
 #endif
+
+/* exp() and log() for the hot loops.  Same argument reduction and polynomial degree as any libm, but
+ * the coefficients are operands from constant memory: the CUDA math library materialises every double
+ * constant with two move instructions, which made ~2/3 of the ~75 instructions of each exp/log call
+ * (SASS of the first builds; UMOV + IMAD.MOV were 20 % of k_fit's instructions).
+ *   ns_fexp: finite x; underflows to 0 below -708 (no denormals), Taylor to r^13 on |r| <= ln2/2: < 1 ulp
+ *   ns_flog: normal positive x; the fdlibm scheme  log(1+f) = f - (f^2/2 - s*(f^2/2 + R(s^2))), s = f/(2+f) */
+#define NS_EXPC_INIT {1.6059043836821613e-10, 2.08767569878681e-09, 2.505210838544172e-08, 2.755731922398589e-07, 2.7557319223985893e-06, 2.48015873015873e-05, 0.0001984126984126984, 0.001388888888888889, 0.008333333333333333, 0.041666666666666664, 0.16666666666666666, 0.5}
+#define NS_LOGC_INIT                                                                               \
+    {6.666666666666735130e-01, 3.999999999940941908e-01, 2.857142874366239149e-01,                 \
+     2.222219843214978396e-01, 1.818357216161805012e-01, 1.531383769920937332e-01,                 \
+     1.479819860511658591e-01}
+#if defined(__CUDACC__)
+static __constant__ double ns_d_expc[12] = NS_EXPC_INIT;
+static __constant__ double ns_d_logc[7] = NS_LOGC_INIT;
+#endif
+static const double ns_h_expc[12] = NS_EXPC_INIT;
+static const double ns_h_logc[7] = NS_LOGC_INIT;
+
+NS_HD double ns_fexp(double x)
+{
+    if (!(x > -708.0))
+        return (x != x) ? x : 0.0;
+    const double MAGIC = 6755399441055744.0; /* 1.5 * 2^52: rounds to nearest integer in the low bits */
+    double kd = fma(x, 1.4426950408889634074, MAGIC);
+    long long kb;
+    memcpy(&kb, &kd, sizeof kb);
+    const int k = (int)(kb & 0xffffffffLL); /* low 32 bits hold the integer (two's complement) */
+    kd -= MAGIC;
+    double r = fma(-kd, 6.93147180369123816490e-01, x);
+    r = fma(-kd, 1.90821492927058770002e-10, r);
+    double p = NS_TBL(expc)[0];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int i = 1; i < 12; i++)
+        p = fma(p, r, NS_TBL(expc)[i]);
+    p = fma(p, r, 1.0);
+    p = fma(p, r, 1.0);
+    long long pb;
+    memcpy(&pb, &p, sizeof pb);
+    pb += (long long)k << 52; /* p in [0.7, 1.42], k >= -1022: stays normal */
+    memcpy(&p, &pb, sizeof p);
+    return p;
+}
+
+NS_HD double ns_flog(double x)
+{
+    long long xb;
+    memcpy(&xb, &x, sizeof xb);
+    int k = (int)(xb >> 52) - 1023;
+    long long mb = (xb & 0x000fffffffffffffLL) | 0x3ff0000000000000LL; /* m in [1, 2) */
+    double m;
+    memcpy(&m, &mb, sizeof m);
+    if (m > 1.41421356237309504880) {
+        m *= 0.5;
+        k += 1;
+    }
+    const double f = m - 1.0;
+    const double s = f * ns_frcp(2.0 + f);
+    const double z = s * s, w = z * z;
+    const double t1 = w * fma(w, fma(w, NS_TBL(logc)[5], NS_TBL(logc)[3]), NS_TBL(logc)[1]);
+    const double t2 = z * fma(w, fma(w, fma(w, NS_TBL(logc)[6], NS_TBL(logc)[4]), NS_TBL(logc)[2]), NS_TBL(logc)[0]);
+    const double R = t2 + t1;
+    const double hfsq = 0.5 * f * f;
+    const double dk = (double)k;
+    return dk * 6.93147180369123816490e-01 - ((hfsq - fma(s, hfsq + R, dk * 1.90821492927058770002e-10)) - f);
+}
 
 /* ---------------------------------------------------------------------------------
  * Loader's saddle-point building blocks (R nmath stirlerr / bd0 / dbinom_raw), the

@@ -57,7 +57,7 @@ struct Chunk {
     const char *beg, *end;
     int64_t n_lines = 0, first_row = 0;
     std::vector<IndelUnit> indels;
-    std::vector<std::string> chroms; /* per line */
+    std::vector<std::pair<std::string, int64_t>> chroms; /* run-length: (name, first row) */
     std::string err;
 };
 
@@ -144,7 +144,9 @@ void parse_chunk(Chunk &ck, ns_table *t)
         }
         /* chr, loc, ref */
         const char *q = next_tab(p, le);
-        ck.chroms.emplace_back(p, q);
+        if (ck.chroms.empty() || ck.chroms.back().first.size() != (size_t)(q - p) ||
+            memcmp(ck.chroms.back().first.data(), p, (size_t)(q - p)) != 0)
+            ck.chroms.emplace_back(std::string(p, q), row);
         const char *f = q + 1;
         q = next_tab(f, le);
         int64_t loc = 0;
@@ -167,20 +169,27 @@ void parse_chunk(Chunk &ck, ns_table *t)
         const size_t first_unit = ck.indels.size();
         int64_t cov_ins = 0, cov_del = 0;
         for (int s = 0; s < n; s++) {
+            /* nine count fields: hand-rolled scan (fields are 1-3 characters, memchr per field dominates) */
+            const char *c = q;
             for (int k = 0; k < 9; k++) {
-                if (q >= le) {
+                if (c >= le) {
                     ck.err = "too few columns (expected 3 + 11 per sample)";
                     return;
                 }
-                f = q + 1;
-                q = next_tab(f, le);
-                int32_t v;
-                if (!parse_int(f, q, v)) {
+                ++c; /* the tab */
+                uint32_t v = 0;
+                const char *f0 = c;
+                while (c < le && (unsigned)(*c - '0') <= 9u) {
+                    v = v * 10u + (unsigned)(*c - '0');
+                    ++c;
+                }
+                if (c == f0 || (c < le && *c != '\t') || c - f0 > 9) {
                     ck.err = "non-integer count field";
                     return;
                 }
-                dst[(size_t)k * n + s] = v;
+                dst[(size_t)k * n + s] = (int32_t)v;
             }
+            q = c;
             /* insertion cell, then deletion cell (needlestack.r:197-198) */
             for (int k = 0; k < 2; k++) {
                 if (q >= le) {
@@ -313,8 +322,8 @@ ns_table *ns_table_parse(const char *text, size_t len, int n_samples, int has_he
         }
     /* chromosome dictionary in order of first appearance; indel units concatenated in input order */
     for (auto &ck : cks) {
-        int64_t row = ck.first_row;
-        for (auto &c : ck.chroms) {
+        for (size_t r = 0; r < ck.chroms.size(); r++) {
+            const std::string &c = ck.chroms[r].first;
             int32_t id = -1;
             for (int32_t k = (int32_t)t->chrom_names.size() - 1; k >= 0; k--)
                 if (t->chrom_names[(size_t)k] == c) {
@@ -325,7 +334,10 @@ ns_table *ns_table_parse(const char *text, size_t len, int n_samples, int has_he
                 id = (int32_t)t->chrom_names.size();
                 t->chrom_names.push_back(c);
             }
-            t->chrom[(size_t)row++] = id;
+            const int64_t r0 = ck.chroms[r].second;
+            const int64_t r1 = r + 1 < ck.chroms.size() ? ck.chroms[r + 1].second : ck.first_row + ck.n_lines;
+            for (int64_t row = r0; row < r1; row++)
+                t->chrom[(size_t)row] = id;
         }
         for (auto &u : ck.indels) {
             t->iu_pos.push_back(u.pos_index);

@@ -1,2 +1,5 @@
 make -s -C oracle
-python tests/parity_at_scale.py gpurun_out/parity_r1.json 2>&1 | grep -o '"ok": [a-z]*.*"config": "C[0-9]"' | cut -c1-80
+python -m pytest tests -q -m gpu -x 2>&1 | tail -3
+python bench.py --steps 3 --warmup 2 --positions 200000 --no-cpu --no-e2e --p-germline 0 2>/dev/null | python -c "
+import json,sys
+d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('nogerm', round(d['value']), round(d['ms_per_step'],1), {k:round(v,1) for k,v in d['detail']['kernel_ms_per_step_rank0'].items()}, 'frac', round(d['roofline']['frac'],3))"

@@ -88,6 +88,8 @@ int emul_unit(int n, const int32_t *dp, const int32_t *vp, const int32_t *vm, co
 double emul_dnbinom_mu(double x, double size, double mu) { return ns_dnbinom_mu(x, size, mu); }
 double emul_nb_pvalue(double y, double size, double mu) { return ns_nb_pvalue(y, size, mu); }
 double emul_digamma(double x) { return ns_digamma(x); }
+double emul_fexp(double x) { return ns_fexp(x); }
+double emul_flog(double x) { return ns_flog(x); }
 double emul_qnbinom_mu(double p, double size, double mu) { return ns_qnbinom_mu(p, size, mu); }
 double emul_qbinom(double p, double n, double pr) { return ns_qbinom(p, n, pr); }
 double emul_fisher(double a, double b, double c, double d) { return ns_fisher_2x2(a, b, c, d); }
