@@ -23,6 +23,28 @@
 #define NS_RTAB 256 /* reciprocals 1/j, j = 1..255 */
 #define NS_STEP_BY 16.0 /* knot spacing up to which the spline knots are reached by lattice recurrence */
 
+/* The hot functions are out of line, so the compiler no longer sees that the working set lives in
+ * shared memory and would emit generic loads (LD + address translation).  In the fast path the
+ * tables and per-sample arrays are read through explicit shared-space loads. */
+#if defined(__CUDA_ARCH__)
+struct ns_sptr {
+    unsigned a;
+    __device__ __forceinline__ explicit ns_sptr(const double *p) : a((unsigned)__cvta_generic_to_shared(p)) {}
+    __device__ __forceinline__ double operator[](int i) const
+    {
+        double v;
+        asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a + 8u * (unsigned)i));
+        return v;
+    }
+};
+#else
+struct ns_sptr {
+    const double *p;
+    explicit ns_sptr(const double *q) : p(q) {}
+    double operator[](int i) const { return p[i]; }
+};
+#endif
+
 struct ns_fit_counters {
     unsigned long long n_seed, n_lattice, n_quad;
     int quad_err;      /* an integrate() that R would have raised as an error */
@@ -310,14 +332,16 @@ NS_GFN double ns_sig_objective(double sig, const ns_work &w, int n, const ns_par
         double dg0 = 0;
         bool have_dg0 = false;
         const double twon = (double)(2 * prm.n_ai_sig_tukey);
+        const ns_sptr s_x(w.x), s_mu(w.mu), s_y(w.y), s_dtab(w.dtab), s_r2(w.r2tab);
+        unsigned n_seed = 0, n_lat = 0; /* kept in registers, added to cnt once */
         for (int i = G::lane(); i < n; i += G::nl()) {
-            if (!(w.x[i] > 0))
+            if (!(s_x[i] > 0))
                 continue;
-            const double mu = w.mu[i], y = w.y[i];
+            const double mu = s_mu[i], y = s_y[i];
             const double s1 = sig * mu + 1;
             const double sd = ns_fsqrt(mu * s1);
             const double j1 = fmax(ceil(mu - c * sd), 0.0), j2 = floor(mu + c * sd);
-            cnt.n_seed += 1;
+            n_seed += 1;
             double term;
             if (j1 == 0 && j2 < (double)NS_JTAB) {
                 /* window {0..j2}: everything by recurrence, no division inside the loop.
@@ -337,14 +361,14 @@ NS_GFN double ns_sig_objective(double sig, const ns_work &w, int n, const ns_par
                     const double wpsi = wt * fma(-jd, inv_mpi, D);
                     a = fma(wpsi, pm, a);
                     ty = (j == yi) ? wpsi : ty; /* (psi_c(r)/r) * psi.sig.ML(r) at r = (y-mu)/sd */
-                    pm *= w.r2tab[j] * q;
-                    D += w.dtab[j];
+                    pm *= s_r2[j] * q;
+                    D += s_dtab[j];
                     jd += 1.0;
                 }
                 term = ty - a;
                 if (y == mu)
                     term = NAN; /* r == 0: tukeypsi(r)/r = 0/0 in R */
-                cnt.n_lattice += (unsigned long long)(J2 + 1);
+                n_lat += (unsigned)(J2 + 1);
             } else if (j1 > j2) {
                 term = 0; /* cannot happen: kept for fidelity */
                 double r = (y - mu) / sd;
@@ -368,10 +392,12 @@ NS_GFN double ns_sig_objective(double sig, const ns_work &w, int n, const ns_par
                     term = wi * psiML;
                 }
                 term -= NS_AI_SUM_OOL(mu, sig, c, j1, j2, dg0);
-                cnt.n_lattice += (unsigned long long)(j2 - j1 + 1);
+                n_lat += (unsigned)(j2 - j1 + 1);
             }
             acc += term;
         }
+        cnt.n_seed += n_seed;
+        cnt.n_lattice += n_lat;
     } else {
         const double dg0 = ns_digamma(invsig);
         for (int i = G::lane(); i < n; i += G::nl()) {
@@ -518,16 +544,18 @@ NS_GFN double ns_irls_step(double sig, const ns_work &w, int n, double maxmu, co
     const double twon = (double)(2 * prm.n_ai_sig_tukey);
     double sw = 0, swz = 0;
     int nanrows = 0;
+    const ns_sptr s_x(w.x), s_mu(w.mu), s_y(w.y), s_eta(w.eta), s_X(w.X), s_r2(w.r2tab);
+    unsigned n_seed = 0, n_lat = 0;
     for (int i = lane; i < n; i += G::nl()) {
-        if (!(w.x[i] > 0))
+        if (!(s_x[i] > 0))
             continue;
-        const double mu = w.mu[i], eta = w.eta[i], y = w.y[i];
+        const double mu = s_mu[i], eta = s_eta[i], y = s_y[i];
         double e1, sap;
         const double V = ns_varfunc(mu, sig);
         const double sV = (MODE == 1) ? ns_fsqrt(V) : sqrt(V);
         if (MODE == 1) {
             const double j1 = fmax(ceil(mu - c * sV), 0.0), j2 = floor(mu + c * sV);
-            res.cnt.n_seed += 1;
+            n_seed += 1;
             if (j1 == 0 && j2 < (double)NS_JTAB) {
                 double pm = ns_fexp(-invsig * ns_flog(sig * mu + 1));
                 const double inv_csd = ns_frcp(c * sV);
@@ -543,13 +571,13 @@ NS_GFN double ns_irls_step(double sig, const ns_work &w, int n, double maxmu, co
                     const double wpd = (wt * pm) * d;
                     a1 += wpd;
                     a2 = fma(wpd, d, a2);
-                    pm *= w.r2tab[j] * q;
+                    pm *= s_r2[j] * q;
                     jd += 1.0;
                 }
                 const double isV = ns_frcp(sV);
                 e1 = a1 * isV;
                 sap = a2 * isV;
-                res.cnt.n_lattice += (unsigned long long)(J2 + 1);
+                n_lat += (unsigned)(J2 + 1);
             } else if (j1 > j2) {
                 e1 = 0;
                 sap = 0;
@@ -558,7 +586,7 @@ NS_GFN double ns_irls_step(double sig, const ns_work &w, int n, double maxmu, co
                 continue;
             } else {
                 NS_E12_SUM_OOL(mu, sig, c, j1, j2, e1, sap);
-                res.cnt.n_lattice += (unsigned long long)(j2 - j1 + 1);
+                n_lat += (unsigned)(j2 - j1 + 1);
             }
         } else {
 #if defined(__CUDA_ARCH__)
@@ -585,8 +613,10 @@ NS_GFN double ns_irls_step(double sig, const ns_work &w, int n, double maxmu, co
         if (bi == 0)
             continue; /* lm.wfit(): zero-weight rows excluded */
         sw += bi;
-        swz += bi * (zi - w.X[i]);
+        swz += bi * (zi - s_X[i]);
     }
+    res.cnt.n_seed += n_seed;
+    res.cnt.n_lattice += n_lat;
     sw = G::sum(sw);
     swz = G::sum(swz);
     if (G::any(nanrows))
