@@ -354,6 +354,9 @@ NS_GFN double ns_sig_objective(double sig, const ns_work &w, int n, const ns_par
                 const int J2 = (int)j2;
                 const int yi = (y <= j2) ? (int)y : -1;
                 double a = 0, ty = 0, jd = 0.0, D = C0; /* D = digamma(j+1/sig) - digamma(1/sig) + C0 */
+#if defined(__CUDA_ARCH__)
+#pragma unroll 2
+#endif
                 for (int j = 0; j <= J2; j++) {
                     const double t = fma(jd, inv_csd, t0);
                     double wt = fma(t, t, -1.0);
@@ -563,6 +566,9 @@ NS_GFN double ns_irls_step(double sig, const ns_work &w, int n, double maxmu, co
                 const double t0 = -mu * inv_csd;
                 const int J2 = (int)j2;
                 double a1 = 0, a2 = 0, jd = 0.0;
+#if defined(__CUDA_ARCH__)
+#pragma unroll 2
+#endif
                 for (int j = 0; j <= J2; j++) {
                     const double t = fma(jd, inv_csd, t0);
                     double wt = fma(t, t, -1.0);
