@@ -506,7 +506,8 @@ static int ns_run_chunk(ns_ctx *ctx, const ns_params &dprm, const double *qtab, 
     }
     CK(cudaMemcpyAsync(ctx->h_counters, ctx->counters.p, sizeof(ns_counters), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
-    const int n_rows = ctx->h_counters->n_rows, n_fit = ctx->h_counters->n_fit;
+    const int n_rows = ctx->h_counters->n_rows;
+    const int n_fit = ctx->h_counters->n_light + ctx->h_counters->n_pre;
     ce = ctx->rows.reserve((size_t)(n_rows > 0 ? n_rows : 1), n);
     if (ce != cudaSuccess) {
         ctx->err = std::string("device allocation (result planes) failed: ") + cudaGetErrorString(ce);

@@ -29,34 +29,70 @@ __device__ __forceinline__ bool ns_ratio_ge(int y, int x, double t)
     return yd / (double)x >= t;
 }
 
-__device__ __forceinline__ void ns_gate_commit(const ns_unit_arrays &ua, ns_counters *cnt, const ns_params &prm, int u,
-                                               uint32_t flags, int is_indel, double mu_hint)
+/* per-unit outputs of the gate (written by one lane) and the unit's work-list class, identical in
+ * all lanes: bits 0-1 = 1 warp kernel, 2 cluster kernel, 0 none; bit 2 = needs result rows */
+__device__ __forceinline__ int ns_gate_commit(const ns_unit_arrays &ua, const ns_params &prm, int u, uint32_t flags,
+                                              int is_indel, double mu_hint, bool writer)
 {
     const bool gated = flags & NS_F_GATED, skipped = flags & NS_F_SKIPPED;
     const bool out_all = (!is_indel) && prm.output_all_SNVs;
     const bool need = !skipped && (!gated || prm.emit_mode == NS_EMIT_ALL || out_all);
-    ua.flags[u] = flags;
-    ua.sigma[u] = NAN;
-    ua.slope[u] = NAN;
-    ua.max_gq[u] = 0.0;
-    ua.iters[u] = 0;
-    ua.cycles[u] = 0;
-    ua.needrow[u] = need;
-    ua.emitflag[u] = 0;
+    if (writer) {
+        ua.flags[u] = flags;
+        ua.sigma[u] = NAN;
+        ua.slope[u] = NAN;
+        ua.max_gq[u] = 0.0;
+        ua.iters[u] = 0;
+        ua.cycles[u] = 0;
+        ua.needrow[u] = need;
+        ua.emitflag[u] = 0;
+    }
+    int cls = need ? 4 : 0;
     if (!gated) {
-        atomicAdd(&cnt->n_fit, 1);
         /* A window of the first sigma objective evaluation (sigma = maxsig, c = c.tukey.sig) exceeds
          * 2*n_ai.sig.tukey lattice points once mu*(1 + c*sqrt(maxsig + 1/mu)) does: such units go
          * straight to the cluster-per-unit kernel, which runs next to the warp kernel on its own
-         * stream.  Over-prediction only costs efficiency. */
+         * stream.  Over-prediction only costs efficiency; the threshold is half the switch point
+         * because the slope usually grows from its first estimate. */
         const double kwin = mu_hint * (1.0 + prm.c_tukey_sig * sqrt(prm.maxsig + 1.0 / fmax(mu_hint, 1e-300)));
-        if (kwin > 1.0 * prm.n_ai_sig_tukey) /* half the switch point: the slope usually grows from its first estimate */
-            ua.pre_list[atomicAdd(&cnt->n_pre, 1)] = u;
-        else
-            ua.fit_list[atomicAdd(&cnt->n_light, 1)] = u;
+        cls |= (kwin > 1.0 * prm.n_ai_sig_tukey) ? 2 : 1;
     }
-    if (need)
-        ua.post_list[atomicAdd(&cnt->n_post, 1)] = u;
+    return cls;
+}
+
+/* Appends up to three units per warp (packed classes, 3 bits per unit k = lane) to the work lists:
+ * slots are reserved with shared-memory atomics inside the CTA and ONE global atomic per list per CTA
+ * iteration (per-unit global atomics on three addresses were the gate kernel's bottleneck).
+ * Must be called by all threads of the CTA. */
+__device__ __forceinline__ void ns_gate_insert(int packed, int u_first, int n_units, const ns_unit_arrays &ua,
+                                               ns_counters *cnt)
+{
+    __shared__ int s_cnt[3], s_base[3];
+    const int lane = threadIdx.x & 31;
+    if (threadIdx.x < 3)
+        s_cnt[threadIdx.x] = 0;
+    __syncthreads();
+    int cls = 0, off_l = 0, off_p = 0;
+    const int u = u_first + lane;
+    if (lane < 3 && u < n_units) {
+        cls = (packed >> (3 * lane)) & 7;
+        if (cls & 3)
+            off_l = atomicAdd(&s_cnt[(cls & 3) - 1], 1);
+        if (cls & 4)
+            off_p = atomicAdd(&s_cnt[2], 1);
+    }
+    __syncthreads();
+    if (threadIdx.x < 3) {
+        int *g = threadIdx.x == 0 ? &cnt->n_light : (threadIdx.x == 1 ? &cnt->n_pre : &cnt->n_post);
+        s_base[threadIdx.x] = s_cnt[threadIdx.x] ? atomicAdd(g, s_cnt[threadIdx.x]) : 0;
+    }
+    __syncthreads();
+    if ((cls & 3) == 1)
+        ua.fit_list[s_base[0] + off_l] = u;
+    else if ((cls & 3) == 2)
+        ua.pre_list[s_base[1] + off_l] = u;
+    if (cls & 4)
+        ua.post_list[s_base[2] + off_p] = u;
 }
 
 /* Streaming gate for SNV planes without the extra-robust pre-filter (the caller's default):
@@ -64,17 +100,18 @@ __device__ __forceinline__ void ns_gate_commit(const ns_unit_arrays &ua, ns_coun
  * compares and warp vote / reduce instructions; medians come from counts, not from a sort:
  *   median(x) < c  <=>  both middle order statistics < c  (count(x < c) decides, and when it equals
  *   n/2 for even n the two middle values are max{x < c} and min{x >= c}). */
-__device__ __forceinline__ void ns_gate_position(const ns_unit_src &src, const ns_params &prm, int64_t p, int u_first,
-                                                 int n_units, const ns_unit_arrays &ua, ns_counters *cnt)
+__device__ __forceinline__ int ns_gate_position(const ns_unit_src &src, const ns_params &prm, int64_t p, int u_first,
+                                                int n_units, const ns_unit_arrays &ua)
 {
     const int n = src.n, lane = threadIdx.x & 31;
     const unsigned FULL = 0xffffffffu;
     const int ref = src.ref[p];
     if (ref > 3) {
         if (lane < 3 && u_first + lane < n_units)
-            ns_gate_commit(ua, cnt, prm, u_first + lane, NS_F_SKIPPED | NS_F_GATED, 0, 0.0);
-        return;
+            ns_gate_commit(ua, prm, u_first + lane, NS_F_SKIPPED | NS_F_GATED, 0, 0.0, true);
+        return 0;
     }
+    int packed = 0;
     const int32_t *base = src.counts + p * 9 * (int64_t)n;
     const double mc = prm.min_coverage;
     /* depth row: samples above min_coverage, order statistics around it, max depth */
@@ -148,31 +185,152 @@ __device__ __forceinline__ void ns_gate_position(const ns_unit_src &src, const n
             nf = __reduce_add_sync(FULL, nf);
             mu_hint = nf > 0 ? 1.001 * (double)s / (double)nf * (double)maxx : 0.0;
         }
-        if (lane == 0)
-            ns_gate_commit(ua, cnt, prm, u, flags, 0, mu_hint);
+        packed |= ns_gate_commit(ua, prm, u, flags, 0, mu_hint, lane == 0) << (3 * k);
     }
+    return packed;
 }
 
-__global__ void __launch_bounds__(NS_WPB_GATE * 32)
+/* Same tests with the position's nine rows held in registers (n <= 32*R): all 9*R loads of a warp are
+ * in flight at once (3.6 KB per warp at n = 100), which is what a streaming kernel needs to approach
+ * the HBM rate; the per-base statistics are computed once and shared by the three alleles. */
+template <int R>
+__device__ __forceinline__ int ns_gate_position_reg(const ns_unit_src &src, const ns_params &prm, int64_t p,
+                                                    int u_first, int n_units, const ns_unit_arrays &ua)
+{
+    const int n = src.n, lane = threadIdx.x & 31;
+    const unsigned FULL = 0xffffffffu;
+    const int32_t *base = src.counts + p * 9 * (int64_t)n;
+    /* issue every load of the position (and the REF code) before anything depends on one of them */
+    int v[9][R];
+#pragma unroll
+    for (int r = 0; r < 9; r++)
+#pragma unroll
+        for (int k = 0; k < R; k++) {
+            const int i = lane + 32 * k;
+            v[r][k] = (i < n) ? __ldg(base + (int64_t)r * n + i) : 0;
+        }
+    const int ref = src.ref[p];
+    if (ref > 3) {
+        if (lane < 3 && u_first + lane < n_units)
+            ns_gate_commit(ua, prm, u_first + lane, NS_F_SKIPPED | NS_F_GATED, 0, 0.0, true);
+        return 0;
+    }
+    int packed = 0;
+    const double mc = prm.min_coverage;
+    int n_cov = 0, n_less = 0, max_less = -1, min_geq = 0x7fffffff, maxx = 0;
+    int cinv[4] = {0, 0, 0, 0}, npos[4] = {0, 0, 0, 0}, mx[4] = {0, 0, 0, 0}, afok[4] = {0, 0, 0, 0};
+    int sy[4] = {0, 0, 0, 0}; /* sum of the base's counts over the lane's samples (fits: <= 4 depths) */
+    long long sx = 0;
+#pragma unroll
+    for (int k = 0; k < R; k++) {
+        const bool in = lane + 32 * k < n;
+        const int x = v[0][k];
+        n_cov += in && (double)x > mc;
+        const bool less = in && (double)x < mc;
+        n_less += less;
+        max_less = less ? max(max_less, x) : max_less;
+        min_geq = (in && !less) ? min(min_geq, x) : min_geq;
+        maxx = max(maxx, x);
+        sx += x;
+#pragma unroll
+        for (int b = 0; b < 4; b++) {
+            const int y = v[1 + b][k] + v[5 + b][k];
+            /* y/x > 0.8 (needlestack.r:330) for integers, exactly: the quotient rounds above the double
+             * 0.8 iff 5y > 4x (a rational y/x != 4/5 is at least 1/(5x) away from it), and y/0 is
+             * Inf (true) for y > 0, NaN (false) for y == 0 — also 5y > 0 */
+            cinv[b] += in && (5LL * (long long)y > 4LL * (long long)x);
+            npos[b] += y > 0;
+            mx[b] = max(mx[b], y);
+            sy[b] += y;
+            if (prm.min_af > 0)
+                afok[b] |= in && ns_ratio_ge(y, x, prm.min_af);
+        }
+    }
+    n_cov = __reduce_add_sync(FULL, n_cov);
+    n_less = __reduce_add_sync(FULL, n_less);
+    max_less = __reduce_max_sync(FULL, max_less);
+    min_geq = __reduce_min_sync(FULL, min_geq);
+    maxx = __reduce_max_sync(FULL, maxx);
+    for (int o = 16; o > 0; o >>= 1)
+        sx += __shfl_xor_sync(FULL, sx, o);
+#pragma unroll
+    for (int b = 0; b < 4; b++) {
+        cinv[b] = __reduce_add_sync(FULL, cinv[b]);
+        npos[b] = __reduce_add_sync(FULL, npos[b]);
+        mx[b] = __reduce_max_sync(FULL, mx[b]);
+        if (prm.min_af > 0)
+            afok[b] = __any_sync(FULL, afok[b]);
+    }
+    bool med_low; /* median(x) < min_coverage */
+    if (n & 1)
+        med_low = n_less >= (n + 1) / 2;
+    else if (n_less >= n / 2 + 1)
+        med_low = true;
+    else if (n_less <= n / 2 - 1)
+        med_low = false;
+    else
+        med_low = ((double)max_less + (double)min_geq) / 2 < mc;
+    const bool pos_gate = med_low || n_cov < prm.size_min;
+    /* static selection of a base's statistics (no dynamically indexed register arrays) */
+#define NS_SEL4(a, b) ((b) == 0 ? a[0] : (b) == 1 ? a[1] : (b) == 2 ? a[2] : a[3])
+    for (int k = 0; k < 3; k++) {
+        const int u = u_first + k;
+        if (u >= n_units)
+            break;
+        const int alt = k + (k >= ref ? 1 : 0);
+        const bool inv = (double)NS_SEL4(cinv, alt) > 0.5 * (double)n; /* needlestack.r:330 */
+        const int yb = inv ? ref : alt;
+        const int np_ = NS_SEL4(npos, yb), maxy = NS_SEL4(mx, yb);
+        bool gate = pos_gate || (double)maxy < prm.min_reads || np_ == 0;
+        if (prm.min_af > 0)
+            gate = gate || !NS_SEL4(afok, yb);
+        const uint32_t flags = (inv ? NS_F_REF_INV : 0u) | (gate ? NS_F_GATED : 0u);
+        double mu_hint = 0;
+        if (!gate) { /* pooled allelic fraction times the largest depth: first-fit mean of the deepest sample */
+            const long long tot = (long long)__reduce_add_sync(FULL, (unsigned)NS_SEL4(sy, yb));
+            mu_hint = sx > 0 ? 1.1 * (double)tot / (double)sx * (double)maxx : 0.0;
+        }
+        packed |= ns_gate_commit(ua, prm, u, flags, 0, mu_hint, lane == 0) << (3 * k);
+    }
+#undef NS_SEL4
+    return packed;
+}
+
+__global__ void __launch_bounds__(NS_WPB_GATE * 32, 3)
 k_gate(ns_unit_src src, ns_params prm, int64_t u0, int n_units, ns_unit_arrays ua, ns_counters *cnt)
 {
     const int n = src.n;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int wstride = gridDim.x * NS_WPB_GATE;
     if (src.mode == 0 && !prm.extra_rob && (u0 % 3) == 0) {
-        /* fast path: warp = position */
+        /* fast path: warp = position (uniform trip count per CTA: the list insertion is a CTA collective) */
         const int n_pos = (n_units + 2) / 3;
-        for (int q = blockIdx.x * NS_WPB_GATE + warp; q < n_pos; q += wstride)
-            ns_gate_position(src, prm, u0 / 3 + q, 3 * q, n_units, ua, cnt);
+        for (int q0 = blockIdx.x * NS_WPB_GATE; q0 < n_pos; q0 += wstride) {
+            const int q = q0 + warp;
+            int packed = 0;
+            if (q < n_pos) {
+                if (n <= 64)
+                    packed = ns_gate_position_reg<2>(src, prm, u0 / 3 + q, 3 * q, n_units, ua);
+                else if (n <= 128)
+                    packed = ns_gate_position_reg<4>(src, prm, u0 / 3 + q, 3 * q, n_units, ua);
+                else
+                    packed = ns_gate_position(src, prm, u0 / 3 + q, 3 * q, n_units, ua);
+            }
+            ns_gate_insert(packed, 3 * q, n_units, ua, cnt);
+        }
         return;
     }
     double *scratch = ns_smem + (size_t)warp * (size_t)n;
-    for (int u = blockIdx.x * NS_WPB_GATE + warp; u < n_units; u += wstride) {
-        ns_rows r = ns_unit_rows(src, u0 + u);
-        double mu_hint = 0;
-        uint32_t flags = ns_gate_unit<WarpG>(r, n, prm, src.plain, scratch, &mu_hint);
-        if (lane == 0)
-            ns_gate_commit(ua, cnt, prm, u, flags, r.is_indel, mu_hint);
+    for (int v0 = blockIdx.x * NS_WPB_GATE; v0 < n_units; v0 += wstride) {
+        const int u = v0 + warp;
+        int packed = 0;
+        if (u < n_units) {
+            ns_rows r = ns_unit_rows(src, u0 + u);
+            double mu_hint = 0;
+            uint32_t flags = ns_gate_unit<WarpG>(r, n, prm, src.plain, scratch, &mu_hint);
+            packed = ns_gate_commit(ua, prm, u, flags, r.is_indel, mu_hint, lane == 0);
+        }
+        ns_gate_insert(packed, u, n_units, ua, cnt);
     }
 }
 
