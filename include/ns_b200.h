@@ -101,7 +101,8 @@ void ns_params_caller_default(ns_params *p);
 typedef struct ns_out {
     /* per unit, length n_units */
     double *sigma, *slope; /* NaN when gated (R: NA) */
-    double *max_gq;        /* max(reg_res$GQ): the VCF QUAL column */
+    double *max_gq;        /* max(reg_res$GQ): the VCF QUAL column.  With NS_EMIT_CALLS it is NaN for units whose
+                              smallest p-value already rules out a call (their multiple-testing step is skipped) */
     uint32_t *flags;       /* NS_F_* */
     uint32_t *iters;       /* n_outer | n_irls << 8 | n_objective_evals << 18 */
     int32_t *emit_index;   /* row in the emitted planes, or -1 */

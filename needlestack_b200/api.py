@@ -143,8 +143,27 @@ class PinnedArray:
 
 
 class Result(dict):
-    """per-unit arrays + emitted rows; attribute access for convenience"""
-    __getattr__ = dict.__getitem__
+    """per-unit arrays + emitted rows; attribute access for convenience.  n_outer / n_irls / n_obj
+    (iteration counts unpacked from `iters`) are computed on first use."""
+
+    def __getattr__(self, k):
+        try:
+            return self[k]
+        except KeyError:
+            raise AttributeError(k)
+
+    def __missing__(self, k):
+        it = dict.__getitem__(self, "iters")
+        if k == "n_outer":
+            v = (it & 0xff).astype(np.int64)
+        elif k == "n_irls":
+            v = ((it >> 8) & 0x3ff).astype(np.int64)
+        elif k == "n_obj":
+            v = (it >> 18).astype(np.int64)
+        else:
+            raise KeyError(k)
+        self[k] = v
+        return v
 
     def row_of(self, unit):
         r = int(self["emit_index"][unit])
@@ -268,11 +287,8 @@ class Caller:
             for k in ("pvalue", "qvalue", "gq", "qval_minaf", "sor", "rvsb", "fs", "gt", "status", "pooled",
                       "emit_unit"):
                 a[k] = a[k][:E]
-        it = a["iters"]
         a.update(n_emitted=E, n_fitted=int(o.n_fitted), n_gated=int(o.n_gated), n_skipped=int(o.n_skipped),
-                 n_seed=int(o.n_seed), n_lattice=int(o.n_lattice), n_quad=int(o.n_quad),
-                 n_outer=(it & 0xff).astype(np.int64), n_irls=((it >> 8) & 0x3ff).astype(np.int64),
-                 n_obj=(it >> 18).astype(np.int64))
+                 n_seed=int(o.n_seed), n_lattice=int(o.n_lattice), n_quad=int(o.n_quad))
         return Result(a)
 
     def _emit_cap(self, prm, U, emit_cap):

@@ -602,13 +602,27 @@ NS_GF inline uint32_t ns_post_unit(const ns_rows &r, int n, const ns_params &prm
             o.gq[i] = 0;
         }
     } else {
+        double pmin = INFINITY;
         for (int i = lane; i < n; i += G::nl()) {
             double x = ns_ld(r.dp, i);
             double y = inv ? ns_ld(r.rp, i) + ns_ld(r.rm, i) : ns_ld(r.vp, i) + ns_ld(r.vm, i);
             double p = ns_nb_pvalue(y, size, slope * x, rt, rtn);
-            o.pvalue[i] = p;
             tmp[i] = p;
+            pmin = fmin(pmin, p);
         }
+        /* Early out when only the reference's VCF calls are wanted: every BH q-value is >= the smallest
+         * p-value (the factors n/rank are >= 1), so if -10 log10(min p) cannot reach GQ_threshold no sample
+         * passes needlestack.r:381 and nothing of this unit is written.  Its rows and max_gq are then
+         * not computed (max_gq is reported as NaN). */
+        if (prm.emit_mode == NS_EMIT_CALLS && !((!r.is_indel) && prm.output_all_SNVs)) {
+            pmin = -G::max(-pmin);
+            if (-10 * log10(pmin) < thr - 1e-9) {
+                max_gq_out = NAN;
+                return flags;
+            }
+        }
+        for (int i = lane; i < n; i += G::nl())
+            o.pvalue[i] = tmp[i];
         G::sync();
         ns_sort_ranks<G>(tmp, srt, nullptr, n);
         /* p.adjust(p, "BH") (:222): q_(k) = min(1, min_{j>=k} n/(j+1)*p_(j)), ascending ranks.
