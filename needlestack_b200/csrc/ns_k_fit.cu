@@ -98,7 +98,10 @@ k_fit(ns_unit_src src, ns_params prm, int64_t u0, ns_unit_arrays ua, ns_counters
 /* One thread-block cluster per unit: the CTAs of the cluster split the unit's samples, every
  * warp takes one sample at a time and its lanes share that sample's window (ns_coop.cuh); sums
  * over samples are exchanged through distributed shared memory (ClusterG). */
-__global__ void __launch_bounds__(NS_HEAVY_THREADS, 1)
+#ifndef NS_HEAVY_MINB
+#define NS_HEAVY_MINB 1 /* 128 registers; 64 (to leave half the register file to the warp kernel) spills and is 1.8x slower */
+#endif
+__global__ void __launch_bounds__(NS_HEAVY_THREADS, NS_HEAVY_MINB)
 k_fit_heavy(ns_unit_src src, ns_params prm, int64_t u0, ns_unit_arrays ua, ns_counters *cnt, int which, int *started)
 {
     const int n = src.n;

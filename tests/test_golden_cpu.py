@@ -77,3 +77,20 @@ def test_window_expectations_sum_and_spline_branches():
             assert abs(e1.value - np.sum(w * (j - mu) * pm) / sd) <= 1e-12 * max(1, abs(e1.value))
             assert abs(e2.value - np.sum(w * (j - mu) ** 2 * pm) / sd) <= 1e-12 * max(1, abs(e2.value))
         assert np.isfinite(ai)
+
+
+def test_calls_mode_early_out_keeps_the_calls():
+    """NS_EMIT_CALLS skips the multiple-testing step of units whose smallest p-value rules out a call:
+    the gate flags and every row of the units that ARE calls must be unchanged"""
+    from needlestack_b200 import _abi
+    G = golden_util.load("c1_default")
+    full = parity.emul_snv_batch(emul, G["ref"], G["counts"], emul.make_params(emit_mode=_abi.NS_EMIT_ALL))
+    calls = parity.emul_snv_batch(emul, G["ref"], G["counts"], emul.make_params(emit_mode=_abi.NS_EMIT_CALLS))
+    g = _abi.NS_F_GATE1 | _abi.NS_F_GATE2 | _abi.NS_F_GATED | _abi.NS_F_REF_INV
+    assert np.array_equal(full["flags"] & g, calls["flags"] & g)
+    sel = (full["flags"] & _abi.NS_F_GATE1) != 0
+    assert sel.sum() > 3
+    for k in ("gq", "qval_minaf", "sor", "gt", "status", "max_gq"):
+        assert np.array_equal(full[k][sel], calls[k][sel], equal_nan=True), k
+    skipped = ((full["flags"] & (_abi.NS_F_GATED | _abi.NS_F_GATE1)) == 0)
+    assert np.all(np.isnan(calls["max_gq"][skipped]) | (calls["max_gq"][skipped] < 50))
