@@ -399,7 +399,7 @@ static cudaError_t ns_reserve_units(ns_ctx *ctx, size_t U)
 }
 
 /* geometry of the cluster-per-unit kernel: threads per CTA and CTAs per cluster */
-static void ns_heavy_geometry(int n, int *threads, int *cl)
+static void ns_heavy_geometry(int n, int n_units, int sm_count, int *threads, int *cl)
 {
     int th = NS_HEAVY_THREADS;
     const char *eth = getenv("NS_HEAVY_THREADS");
@@ -409,6 +409,10 @@ static void ns_heavy_geometry(int n, int *threads, int *cl)
     int c = 1;
     while (c < 8 && c * wpc < n)
         c <<= 1; /* enough warps for one sample per warp, up to the portable cluster size 8 */
+    /* many queued units (deep panels: every unit takes this kernel): throughput matters more than the
+     * latency of one unit, and smaller clusters waste fewer warps at the barriers */
+    while (c > 1 && n_units > 8 * (sm_count / c))
+        c >>= 1;
     const char *ecl = getenv("NS_HEAVY_CLUSTER");
     if (ecl && atoi(ecl) >= 1 && atoi(ecl) <= 16)
         c = atoi(ecl);
@@ -427,7 +431,7 @@ static cudaError_t ns_launch_heavy(ns_ctx *ctx, cudaStream_t st, int n, int n_un
                                    int *n_clusters_out)
 {
     int threads, cl;
-    ns_heavy_geometry(n, &threads, &cl);
+    ns_heavy_geometry(n, n_units_max, ctx->sm_count, &threads, &cl);
     const size_t smh = ns_heavy_smem(n, threads);
     cudaError_t e;
     if (smh > 48 * 1024 && (e = cudaFuncSetAttribute(k_fit_heavy, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smh)))
@@ -520,7 +524,7 @@ static int ns_run_chunk(ns_ctx *ctx, const ns_params &dprm, const double *qtab, 
     bool heavy_forked = false;
     if (n_fit > 0) {
         int hth, hcl;
-        ns_heavy_geometry(n, &hth, &hcl);
+        ns_heavy_geometry(n, 1, ctx->sm_count, &hth, &hcl);
         if (ns_heavy_smem(n, hth) > 227 * 1024) {
             ctx->err = "too many samples for the heavy kernel's working set";
             return NS_ERR_ARG;
