@@ -245,27 +245,6 @@ NS_GF inline void ns_E_tukeypsi_12(double mui, double sig, double c, int n_ai, n
     ns_E12_sum(mui, sig, c, j1, j2, e1, e2);
 }
 
-#if defined(__CUDACC__)
-/* out-of-line copies for the rare medium-length windows of the fast kernel */
-static __host__ __device__ __noinline__ double ns_ai_sum_ool(double mui, double sig, double c, double j1, double j2, double dg0)
-{
-    return ns_ai_sum(mui, sig, c, j1, j2, dg0);
-}
-static __host__ __device__ __noinline__ void ns_E12_sum_ool(double mui, double sig, double c, double j1, double j2, double *e1,
-                                            double *e2)
-{
-    ns_E12_sum(mui, sig, c, j1, j2, *e1, *e2);
-}
-static __host__ __device__ __noinline__ double ns_digamma_ool(double x) { return ns_digamma(x); }
-#define NS_AI_SUM_OOL ns_ai_sum_ool
-#define NS_E12_SUM_OOL(mu, sig, c, j1, j2, e1, e2) ns_E12_sum_ool(mu, sig, c, j1, j2, &(e1), &(e2))
-#define NS_DIGAMMA_OOL ns_digamma_ool
-#else
-#define NS_AI_SUM_OOL ns_ai_sum
-#define NS_E12_SUM_OOL(mu, sig, c, j1, j2, e1, e2) ns_E12_sum(mu, sig, c, j1, j2, e1, e2)
-#define NS_DIGAMMA_OOL ns_digamma
-#endif
-
 /* warp-cooperative versions for the heavy kernel (ns_coop.cuh, device only) */
 struct ns_coop_scratch {
     double *y, *c, *ib, *m; /* NS_MAX_KNOTS each, per warp, shared memory */
@@ -317,6 +296,111 @@ struct ns_fit_result {
 #define NS_GFN
 #endif
 
+/* ---- fast path (MODE 1): two samples per lane in flight ------------------------------------
+ * The per-sample chains (rsqrt/log/exp seed, pmf recurrence) are long and dependent; ncu showed the
+ * warp kernel waiting on fixed-latency dependencies (stall_wait 3 of 7 cycles per issue).  Each lane
+ * therefore carries samples i and i+nl through the seed and one joint window loop. */
+NS_HD double ns_tukeypsi_f(double r, double c, double inv_c)
+{ /* tukeypsi with the division by c as a multiplication; NaN propagates */
+    double t = r * inv_c;
+    t = fma(t, t, -1.0);
+    const double v = t * t * r;
+    return (fabs(r) > c) ? 0.0 : v;
+}
+
+/* Tukey's biweight (t^2-1)^2 inside |t| <= 1 and 0 outside, from u = t^2-1: a positive u loses its
+ * high word (u*u then underflows to 0) with two integer instructions, so the joint window loop of two
+ * samples needs no end-of-window test.  At the window's ends (|t| = 1 up to rounding) the weight is 0
+ * either way. */
+#if defined(__CUDA_ARCH__)
+__device__ __forceinline__ double ns_biweight(double u)
+{
+    int hi = __double2hiint(u);
+    hi &= hi >> 31;
+    u = __hiloint2double(hi, __double2loint(u));
+    return u * u;
+}
+#define NS_UNROLL1 _Pragma("unroll 1")
+#else
+static inline double ns_biweight(double u) { return u <= 0.0 ? u * u : 0.0; }
+#define NS_UNROLL1
+#endif
+
+struct ns_fseed {
+    double mu, y, s1, sd, isd, pm, ics, t0;
+    int J2;    /* last lattice point of the window {0..J2}; -1: nothing to sum here */
+    bool slow; /* valid sample whose window is not of the {0..J2 < NS_JTAB} shape */
+};
+/* quantities shared by ai.sig.tukey and E.tukeypsi.1/.2 on a window that starts at 0:
+ * sd = sqrt(V), isd = 1/sd, pm = dnbinom(0) = (1+sig mu)^(-1/sig), t_j = t0 + j*ics */
+NS_HD void ns_fast_seed(ns_fseed &S, bool valid, double sig, double invsig, double c, double inv_c, double &lg)
+{
+    S.s1 = fma(sig, S.mu, 1.0);
+    ns_fsqrt2(S.mu * S.s1, S.sd, S.isd);
+    const double csd = c * S.sd;
+    const double hi = S.mu + csd, lo = S.mu - csd;
+    const bool shape = (lo <= 0.0) && (hi < (double)NS_JTAB); /* j1 == 0 and j2 < NS_JTAB */
+    S.slow = valid && !shape;
+    S.J2 = (valid && shape) ? ns_d2i_floor(hi) : -1;
+    lg = ns_flog(S.s1);
+    S.pm = ns_fexp_bf(-invsig * lg);
+    S.ics = S.isd * inv_c;
+    S.t0 = -S.mu * S.ics;
+}
+
+/* a sample of the warp kernel whose window is not {0..J2<NS_JTAB}: generic lattice sum, or hand-over */
+static NS_HDN double ns_obj_slow(double mu, double y, double sig, double c, double twon, double *dg0, int *have_dg0,
+                                 int *need_heavy, unsigned *n_lat)
+{
+    const double invsig = 1 / sig;
+    const double sd = sqrt(mu * (sig * mu + 1));
+    const double j1 = fmax(ceil(mu - c * sd), 0.0), j2 = floor(mu + c * sd);
+    double term;
+    if (j1 > j2) {
+        term = 0; /* cannot happen: kept for fidelity */
+        double r = (y - mu) / sd;
+        double wi = ns_tukeypsi(r, c) / r;
+        if (wi != 0.0)
+            term = NAN;
+    } else if (j2 - j1 + 1 > twon) {
+        *need_heavy = 1;
+        term = 0;
+    } else {
+        if (!*have_dg0) {
+            *dg0 = ns_digamma(invsig);
+            *have_dg0 = 1;
+        }
+        double r = (y - mu) / sqrt(ns_varfunc(mu, sig));
+        double wi = ns_tukeypsi(r, c) / r;
+        term = 0.0;
+        if (wi != 0.0) {
+            double psiML = ns_digamma(r * sqrt(mu * (sig * mu + 1)) + mu + invsig) - sig * r * sqrt(mu / (sig * mu + 1)) -
+                           *dg0 - log(sig * mu + 1);
+            term = wi * psiML;
+        }
+        term -= ns_ai_sum(mu, sig, c, j1, j2, *dg0);
+        *n_lat += (unsigned)(j2 - j1 + 1);
+    }
+    return term;
+}
+
+/* same for the IRLS pass: returns 0 when the sample needs the heavy kernel */
+static NS_HDN int ns_irls_slow(double mu, double sig, double c, double twon, double *e1, double *sap, unsigned *n_lat)
+{
+    const double sV = sqrt(ns_varfunc(mu, sig));
+    const double j1 = fmax(ceil(mu - c * sV), 0.0), j2 = floor(mu + c * sV);
+    if (j1 > j2) {
+        *e1 = 0;
+        *sap = 0;
+    } else if (j2 - j1 + 1 > twon) {
+        return 0;
+    } else {
+        ns_E12_sum(mu, sig, c, j1, j2, *e1, *sap);
+        *n_lat += (unsigned)(j2 - j1 + 1);
+    }
+    return 1;
+}
+
 /* out of line on purpose: three call sites in the Brent driver; inlining them tripled the kernel's
  * code and the warps stalled on instruction fetch (ncu: 32 % of issue stalls) */
 template <class G, int MODE>
@@ -330,75 +414,69 @@ NS_GFN double ns_sig_objective(double sig, const ns_work &w, int n, const ns_par
     if (MODE == 1) {
         G::fill_dtab(w.dtab, w.r2tab, w.rtab, invsig, NS_JTAB);
         double dg0 = 0;
-        bool have_dg0 = false;
+        int have_dg0 = 0;
         const double twon = (double)(2 * prm.n_ai_sig_tukey);
+        const double inv_c = 1.0 / c;
         const ns_sptr s_x(w.x), s_mu(w.mu), s_y(w.y), s_dtab(w.dtab), s_r2(w.r2tab);
         unsigned n_seed = 0, n_lat = 0; /* kept in registers, added to cnt once */
-        for (int i = G::lane(); i < n; i += G::nl()) {
-            if (!(s_x[i] > 0))
-                continue;
-            const double mu = s_mu[i], y = s_y[i];
-            const double s1 = sig * mu + 1;
-            const double sd = ns_fsqrt(mu * s1);
-            const double j1 = fmax(ceil(mu - c * sd), 0.0), j2 = floor(mu + c * sd);
-            n_seed += 1;
-            double term;
-            if (j1 == 0 && j2 < (double)NS_JTAB) {
-                /* window {0..j2}: everything by recurrence, no division inside the loop.
-                 * t_j = (j-mu)/(c sd) = t0 + j/(c sd);  psi_j = D_j - lg - (j-mu)/(mu+1/sig) = D_j + C0 - j/(mu+1/sig) */
-                const double lg = ns_flog(s1);
-                double pm = ns_fexp(-invsig * lg); /* dnbinom(0) = (1+sig*mu)^(-1/sig) */
-                const double inv_csd = ns_frcp(c * sd), inv_mpi = ns_frcp(mu + invsig);
-                const double q = mu * inv_mpi;
-                const double t0 = -mu * inv_csd, C0 = mu * inv_mpi - lg;
-                const int J2 = (int)j2;
-                const int yi = (y <= j2) ? (int)y : -1;
-                double a = 0, ty = 0, jd = 0.0, D = C0; /* D = digamma(j+1/sig) - digamma(1/sig) + C0 */
-#if defined(__CUDA_ARCH__)
-#pragma unroll 2
-#endif
-                for (int j = 0; j <= J2; j++) {
-                    const double t = fma(jd, inv_csd, t0);
-                    double wt = fma(t, t, -1.0);
-                    wt *= wt;
-                    const double wpsi = wt * fma(-jd, inv_mpi, D);
-                    a = fma(wpsi, pm, a);
-                    ty = (j == yi) ? wpsi : ty; /* (psi_c(r)/r) * psi.sig.ML(r) at r = (y-mu)/sd */
-                    pm *= s_r2[j] * q;
-                    D += s_dtab[j];
-                    jd += 1.0;
-                }
-                term = ty - a;
-                if (y == mu)
-                    term = NAN; /* r == 0: tukeypsi(r)/r = 0/0 in R */
-                n_lat += (unsigned)(J2 + 1);
-            } else if (j1 > j2) {
-                term = 0; /* cannot happen: kept for fidelity */
-                double r = (y - mu) / sd;
-                double wi = ns_tukeypsi(r, c) / r;
-                if (wi != 0.0)
-                    term = NAN;
-            } else if (j2 - j1 + 1 > twon) {
-                need_heavy = 1;
-                term = 0;
-            } else {
-                if (!have_dg0) {
-                    dg0 = NS_DIGAMMA_OOL(invsig);
-                    have_dg0 = true;
-                }
-                double r = (y - mu) / sqrt(ns_varfunc(mu, sig));
-                double wi = ns_tukeypsi(r, c) / r;
-                term = 0.0;
-                if (wi != 0.0) {
-                    double psiML = NS_DIGAMMA_OOL(r * sqrt(mu * (sig * mu + 1)) + mu + invsig) -
-                                   sig * r * sqrt(mu / (sig * mu + 1)) - dg0 - log(sig * mu + 1);
-                    term = wi * psiML;
-                }
-                term -= NS_AI_SUM_OOL(mu, sig, c, j1, j2, dg0);
-                n_lat += (unsigned)(j2 - j1 + 1);
+        const int nl = G::nl();
+        double accB = 0;
+        for (int iA = G::lane(); iA < n; iA += 2 * nl) {
+            const int iB = (iA + nl < n) ? iA + nl : iA;
+            const bool vA = s_x[iA] > 0, vB = (iB != iA) && (s_x[iB] > 0);
+            ns_fseed A, B;
+            A.mu = vA ? s_mu[iA] : 1.0;
+            A.y = vA ? s_y[iA] : 0.0;
+            B.mu = vB ? s_mu[iB] : 1.0;
+            B.y = vB ? s_y[iB] : 0.0;
+            double lgA, lgB;
+            ns_fast_seed(A, vA, sig, invsig, c, inv_c, lgA);
+            ns_fast_seed(B, vB, sig, invsig, c, inv_c, lgB);
+            /* window {0..J2}: everything by recurrence, no division inside the loop.
+             * t_j = (j-mu)/(c sd) = t0 + j/(c sd);  psi_j = D_j - lg - (j-mu)/(mu+1/sig) = D_j + C0 - j/(mu+1/sig),
+             * 1/(mu+1/sig) = sig/(1+sig mu) = sig mu / V */
+            const double impA = (sig * A.mu) * (A.isd * A.isd), impB = (sig * B.mu) * (B.isd * B.isd);
+            const double qA = A.mu * impA, qB = B.mu * impB;
+            /* a y beyond the window meets weight 0 (or no lattice point at all): tukeypsi(r) = 0 there */
+            const int yiA = (A.y < (double)NS_JTAB) ? (int)A.y : NS_JTAB, yiB = (B.y < (double)NS_JTAB) ? (int)B.y : NS_JTAB;
+            double DA = qA - lgA, DB = qB - lgB; /* D = digamma(j+1/sig) - digamma(1/sig) + C0 */
+            double pmA = A.pm, pmB = B.pm, aA = 0, aB = 0, tyA = 0, tyB = 0, jd = 0.0;
+            const int Jm = A.J2 > B.J2 ? A.J2 : B.J2;
+            NS_UNROLL1
+            for (int j = 0; j <= Jm; j++) {
+                const double r2 = s_r2[j], dt = s_dtab[j];
+                const double tA = fma(jd, A.ics, A.t0), tB = fma(jd, B.ics, B.t0);
+                const double wA = ns_biweight(fma(tA, tA, -1.0)), wB = ns_biweight(fma(tB, tB, -1.0));
+                const double wpsiA = wA * fma(-jd, impA, DA), wpsiB = wB * fma(-jd, impB, DB);
+                aA = fma(wpsiA, pmA, aA);
+                aB = fma(wpsiB, pmB, aB);
+                tyA = (j == yiA) ? wpsiA : tyA; /* (psi_c(r)/r) * psi.sig.ML(r) at r = (y-mu)/sd */
+                tyB = (j == yiB) ? wpsiB : tyB;
+                pmA *= r2 * qA;
+                pmB *= r2 * qB;
+                DA += dt;
+                DB += dt;
+                jd += 1.0;
             }
-            acc += term;
+            double termA = tyA - aA, termB = tyB - aB;
+            if (A.y == A.mu)
+                termA = NAN; /* r == 0: tukeypsi(r)/r = 0/0 in R */
+            if (B.y == B.mu)
+                termB = NAN;
+            if (A.J2 < 0)
+                termA = 0; /* no sample here, or one for ns_obj_slow */
+            if (B.J2 < 0)
+                termB = 0;
+            n_seed += (unsigned)vA + (unsigned)vB;
+            n_lat += (unsigned)(A.J2 + 1) + (unsigned)(B.J2 + 1);
+            if (A.slow)
+                termA = ns_obj_slow(A.mu, A.y, sig, c, twon, &dg0, &have_dg0, &need_heavy, &n_lat);
+            if (B.slow)
+                termB = ns_obj_slow(B.mu, B.y, sig, c, twon, &dg0, &have_dg0, &need_heavy, &n_lat);
+            acc += termA;
+            accB += termB;
         }
+        acc += accB;
         cnt.n_seed += n_seed;
         cnt.n_lattice += n_lat;
     } else {
@@ -549,68 +627,93 @@ NS_GFN double ns_irls_step(double sig, const ns_work &w, int n, double maxmu, co
     int nanrows = 0;
     const ns_sptr s_x(w.x), s_mu(w.mu), s_y(w.y), s_eta(w.eta), s_X(w.X), s_r2(w.r2tab);
     unsigned n_seed = 0, n_lat = 0;
+    if (MODE == 1) {
+        /* two samples per lane in flight (see ns_fast_seed).  With y1 = 1/sqrt(V): 1/(V sqrt V) = y1^3,
+         * mu/(mu+1/sig) = sig mu^2 y1^2, V/mu = 1 + sig mu */
+        const double inv_c = 1.0 / c;
+        const int nl = G::nl();
+        for (int iA = lane; iA < n; iA += 2 * nl) {
+            const int iB = (iA + nl < n) ? iA + nl : iA;
+            const bool vA = s_x[iA] > 0, vB = (iB != iA) && (s_x[iB] > 0);
+            ns_fseed A, B;
+            A.mu = vA ? s_mu[iA] : 1.0;
+            A.y = vA ? s_y[iA] : 0.0;
+            B.mu = vB ? s_mu[iB] : 1.0;
+            B.y = vB ? s_y[iB] : 0.0;
+            double lgA, lgB;
+            ns_fast_seed(A, vA, sig, invsig, c, inv_c, lgA);
+            ns_fast_seed(B, vB, sig, invsig, c, inv_c, lgB);
+            const double qA = (sig * A.mu * A.mu) * (A.isd * A.isd), qB = (sig * B.mu * B.mu) * (B.isd * B.isd);
+            double pmA = A.pm, pmB = B.pm, a1A = 0, a2A = 0, a1B = 0, a2B = 0, jd = 0.0;
+            const int Jm = A.J2 > B.J2 ? A.J2 : B.J2;
+            NS_UNROLL1
+            for (int j = 0; j <= Jm; j++) {
+                const double r2 = s_r2[j];
+                const double tA = fma(jd, A.ics, A.t0), tB = fma(jd, B.ics, B.t0);
+                const double wA = ns_biweight(fma(tA, tA, -1.0)), wB = ns_biweight(fma(tB, tB, -1.0));
+                const double dA = jd - A.mu, dB = jd - B.mu;
+                const double wpdA = (wA * pmA) * dA, wpdB = (wB * pmB) * dB;
+                a1A += wpdA;
+                a2A = fma(wpdA, dA, a2A);
+                a1B += wpdB;
+                a2B = fma(wpdB, dB, a2B);
+                pmA *= r2 * qA;
+                pmB *= r2 * qB;
+                jd += 1.0;
+            }
+            double e1A = a1A * A.isd, sapA = a2A * A.isd, e1B = a1B * B.isd, sapB = a2B * B.isd;
+            n_seed += (unsigned)vA + (unsigned)vB;
+            n_lat += (unsigned)(A.J2 + 1) + (unsigned)(B.J2 + 1);
+            bool useA = vA, useB = vB;
+            if (A.slow && !ns_irls_slow(A.mu, sig, c, twon, &e1A, &sapA, &n_lat)) {
+                need_heavy = 1;
+                useA = false;
+            }
+            if (B.slow && !ns_irls_slow(B.mu, sig, c, twon, &e1B, &sapB, &n_lat)) {
+                need_heavy = 1;
+                useB = false;
+            }
+            /* derivinvlink(eta) = exp(log(mu)) = mu */
+            const double biA = sapA * (A.isd * A.isd * A.isd) * (A.mu * A.mu);
+            const double biB = sapB * (B.isd * B.isd * B.isd) * (B.mu * B.mu);
+            const double eiA = (ns_tukeypsi_f((A.y - A.mu) * A.isd, c, inv_c) - e1A) * ns_frcp(sapA) * A.s1;
+            const double eiB = (ns_tukeypsi_f((B.y - B.mu) * B.isd, c, inv_c) - e1B) * ns_frcp(sapB) * B.s1;
+            if (useA) {
+                const double zi = s_eta[iA] + eiA;
+                if (biA != biA || zi != zi) {
+                    nanrows++; /* lm(): na.omit drops the row */
+                } else if (biA != 0) { /* lm.wfit(): zero-weight rows excluded */
+                    sw += biA;
+                    swz += biA * (zi - s_X[iA]);
+                }
+            }
+            if (useB) {
+                const double zi = s_eta[iB] + eiB;
+                if (biB != biB || zi != zi) {
+                    nanrows++;
+                } else if (biB != 0) {
+                    sw += biB;
+                    swz += biB * (zi - s_X[iB]);
+                }
+            }
+        }
+    } else
     for (int i = lane; i < n; i += G::nl()) {
         if (!(s_x[i] > 0))
             continue;
         const double mu = s_mu[i], eta = s_eta[i], y = s_y[i];
         double e1, sap;
         const double V = ns_varfunc(mu, sig);
-        const double sV = (MODE == 1) ? ns_fsqrt(V) : sqrt(V);
-        if (MODE == 1) {
-            const double j1 = fmax(ceil(mu - c * sV), 0.0), j2 = floor(mu + c * sV);
-            n_seed += 1;
-            if (j1 == 0 && j2 < (double)NS_JTAB) {
-                double pm = ns_fexp(-invsig * ns_flog(sig * mu + 1));
-                const double inv_csd = ns_frcp(c * sV);
-                const double q = mu * ns_frcp(mu + invsig);
-                const double t0 = -mu * inv_csd;
-                const int J2 = (int)j2;
-                double a1 = 0, a2 = 0, jd = 0.0;
+        const double sV = sqrt(V);
 #if defined(__CUDA_ARCH__)
-#pragma unroll 2
+        if (MODE == 2)
+            ns_E12_coop(mu, sig, c, prm.n_ai_sig_tukey, w.coop, res.cnt, &e1, &sap);
+        else
 #endif
-                for (int j = 0; j <= J2; j++) {
-                    const double t = fma(jd, inv_csd, t0);
-                    double wt = fma(t, t, -1.0);
-                    wt *= wt;
-                    const double d = jd - mu;
-                    const double wpd = (wt * pm) * d;
-                    a1 += wpd;
-                    a2 = fma(wpd, d, a2);
-                    pm *= s_r2[j] * q;
-                    jd += 1.0;
-                }
-                const double isV = ns_frcp(sV);
-                e1 = a1 * isV;
-                sap = a2 * isV;
-                n_lat += (unsigned)(J2 + 1);
-            } else if (j1 > j2) {
-                e1 = 0;
-                sap = 0;
-            } else if (j2 - j1 + 1 > twon) {
-                need_heavy = 1;
-                continue;
-            } else {
-                NS_E12_SUM_OOL(mu, sig, c, j1, j2, e1, sap);
-                n_lat += (unsigned)(j2 - j1 + 1);
-            }
-        } else {
-#if defined(__CUDA_ARCH__)
-            if (MODE == 2)
-                ns_E12_coop(mu, sig, c, prm.n_ai_sig_tukey, w.coop, res.cnt, &e1, &sap);
-            else
-#endif
-                ns_E_tukeypsi_12(mu, sig, c, prm.n_ai_sig_tukey, res.cnt, e1, sap);
-        }
-        double ee = (MODE == 1) ? mu : exp(eta); /* derivinvlink(eta) = exp(log(mu)) */
-        double bi, ei;
-        if (MODE == 1) {
-            bi = sap * ns_frcp(V * sV) * (ee * ee);
-            ei = (ns_tukeypsi((y - mu) * ns_frcp(sV), c) - e1) * ns_frcp(sap) * V * ns_frcp(mu);
-        } else {
-            bi = sap * (1.0 / (V * sV)) * (ee * ee);
-            ei = (ns_tukeypsi((y - mu) / sV, c) - e1) / sap * V * (1 / mu);
-        }
+            ns_E_tukeypsi_12(mu, sig, c, prm.n_ai_sig_tukey, res.cnt, e1, sap);
+        double ee = exp(eta); /* derivinvlink(eta) = exp(log(mu)) */
+        double bi = sap * (1.0 / (V * sV)) * (ee * ee);
+        double ei = (ns_tukeypsi((y - mu) / sV, c) - e1) / sap * V * (1 / mu);
         double zi = eta + ei;
         if (bi != bi || zi != zi) {
             nanrows++; /* lm(): na.omit drops the row */

@@ -59,9 +59,27 @@ __device__ __forceinline__ double ns_fsqrt(double a)
     s = fma(fma(-s, s, a), 0.5 * y, s);
     return (a > 0.0) ? s : ((a == 0.0) ? 0.0 : NAN);
 }
+/* s = sqrt(a) and y = 1/sqrt(a) from one hardware seed (a normal and positive): every reciprocal the
+ * window sums need (1/sd, 1/(c sd), 1/(mu+1/sig) = sig mu y^2, 1/(V sd) = y^3) is a product of y */
+__device__ __forceinline__ void ns_fsqrt2(double a, double &s, double &y)
+{
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));
+    const double h = 0.5 * a;
+    y = y * fma(-h * y, y, 1.5);
+    y = y * fma(-h * y, y, 1.5);
+    s = a * y;
+    s = fma(fma(-s, s, a), 0.5 * y, s);
+}
+__device__ __forceinline__ int ns_d2i_floor(double a) { return __double2int_rd(a); }
 #else
 static inline double ns_frcp(double a) { return 1.0 / a; }
 static inline double ns_fsqrt(double a) { return sqrt(a); }
+static inline void ns_fsqrt2(double a, double &s, double &y)
+{
+    s = sqrt(a);
+    y = 1.0 / s;
+}
+static inline int ns_d2i_floor(double a) { return (int)floor(a); }
 #endif
 
 /* ---- constant tables: __constant__ on the device, plain statics on the host ---- */
@@ -159,6 +177,33 @@ NS_HD double ns_fexp(double x)
     pb += (long long)k << 52; /* p in [0.7, 1.42], k >= -1022: stays normal */
     memcpy(&p, &pb, sizeof p);
     return p;
+}
+
+/* ns_fexp without the early return (x finite or NaN): straight-line code, so that two calls interleave */
+NS_HD double ns_fexp_bf(double x)
+{
+    const double MAGIC = 6755399441055744.0;
+    const double xc = (x > -708.0) ? x : -708.0;
+    double kd = fma(xc, 1.4426950408889634074, MAGIC);
+    long long kb;
+    memcpy(&kb, &kd, sizeof kb);
+    const int k = (int)(kb & 0xffffffffLL);
+    kd -= MAGIC;
+    double r = fma(-kd, 6.93147180369123816490e-01, xc);
+    r = fma(-kd, 1.90821492927058770002e-10, r);
+    double p = NS_TBL(expc)[0];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int i = 1; i < 12; i++)
+        p = fma(p, r, NS_TBL(expc)[i]);
+    p = fma(p, r, 1.0);
+    p = fma(p, r, 1.0);
+    long long pb;
+    memcpy(&pb, &p, sizeof pb);
+    pb += (long long)k << 52;
+    memcpy(&p, &pb, sizeof p);
+    return (x > -708.0) ? p : ((x != x) ? x : 0.0);
 }
 
 NS_HD double ns_flog(double x)
