@@ -37,7 +37,7 @@ def build(force=False, verbose=False):
         objs.append(obj)
         if not force and os.path.exists(obj) and os.path.getmtime(obj) > max(hmt, os.path.getmtime(src)):
             continue
-        cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", "-o", obj, src]
+        cmd = [nvcc] + NVCC_FLAGS + os.environ.get("NS_NVCC_EXTRA", "").split() + (["-Xptxas", "-v"] if verbose else []) + ["-c", "-o", obj, src]
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     failed = False
     for src, p in procs:

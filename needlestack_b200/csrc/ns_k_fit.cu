@@ -44,7 +44,7 @@ __device__ __forceinline__ void ns_store_fit(const ns_unit_arrays &ua, int u, ui
 #define NS_FIT_MINB 5
 #endif
 __global__ void __launch_bounds__(128, NS_FIT_MINB)
-k_fit(ns_unit_src src, ns_params prm, int64_t u0, ns_unit_arrays ua, ns_counters *cnt)
+k_fit(ns_unit_src src, const __grid_constant__ ns_params prm, int64_t u0, ns_unit_arrays ua, ns_counters *cnt)
 {
     const int n = src.n;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -102,7 +102,7 @@ k_fit(ns_unit_src src, ns_params prm, int64_t u0, ns_unit_arrays ua, ns_counters
 #define NS_HEAVY_MINB 1 /* 128 registers; 64 (to leave half the register file to the warp kernel) spills and is 1.8x slower */
 #endif
 __global__ void __launch_bounds__(NS_HEAVY_THREADS, NS_HEAVY_MINB)
-k_fit_heavy(ns_unit_src src, ns_params prm, int64_t u0, ns_unit_arrays ua, ns_counters *cnt, int which, int *started)
+k_fit_heavy(ns_unit_src src, const __grid_constant__ ns_params prm, int64_t u0, ns_unit_arrays ua, ns_counters *cnt, int which, int *started)
 {
     const int n = src.n;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;

@@ -42,8 +42,8 @@ struct ns_unit_arrays {
 
 
 __global__ void k_gate(ns_unit_src src, ns_params prm, int64_t u0, int n_units, ns_unit_arrays ua, ns_counters *cnt);
-__global__ void k_fit(ns_unit_src src, ns_params prm, int64_t u0, ns_unit_arrays ua, ns_counters *cnt);
-__global__ void k_fit_heavy(ns_unit_src src, ns_params prm, int64_t u0, ns_unit_arrays ua, ns_counters *cnt,
+__global__ void k_fit(ns_unit_src src, const __grid_constant__ ns_params prm, int64_t u0, ns_unit_arrays ua, ns_counters *cnt);
+__global__ void k_fit_heavy(ns_unit_src src, const __grid_constant__ ns_params prm, int64_t u0, ns_unit_arrays ua, ns_counters *cnt,
                             int which, int *started);
 __global__ void k_post(ns_unit_src src, ns_params prm, int64_t u0, ns_unit_arrays ua, ns_planes pl,
                        const double *qtab, int qtab_len, ns_counters *cnt);

@@ -181,15 +181,14 @@ NS_HD double ns_fexp(double x)
 
 /* ns_fexp without the early return (x finite or NaN): straight-line code, so that two calls interleave */
 NS_HD double ns_fexp_bf(double x)
-{
+{ /* |x| < 2^31; below -708 the scaled bits are meaningless and the select returns 0 */
     const double MAGIC = 6755399441055744.0;
-    const double xc = (x > -708.0) ? x : -708.0;
-    double kd = fma(xc, 1.4426950408889634074, MAGIC);
+    double kd = fma(x, 1.4426950408889634074, MAGIC);
     long long kb;
     memcpy(&kb, &kd, sizeof kb);
     const int k = (int)(kb & 0xffffffffLL);
     kd -= MAGIC;
-    double r = fma(-kd, 6.93147180369123816490e-01, xc);
+    double r = fma(-kd, 6.93147180369123816490e-01, x);
     r = fma(-kd, 1.90821492927058770002e-10, r);
     double p = NS_TBL(expc)[0];
 #if defined(__CUDA_ARCH__)
@@ -199,11 +198,11 @@ NS_HD double ns_fexp_bf(double x)
         p = fma(p, r, NS_TBL(expc)[i]);
     p = fma(p, r, 1.0);
     p = fma(p, r, 1.0);
-    long long pb;
+    unsigned long long pb;
     memcpy(&pb, &p, sizeof pb);
-    pb += (long long)k << 52;
+    pb += (unsigned long long)(unsigned)k << 52;
     memcpy(&p, &pb, sizeof p);
-    return (x > -708.0) ? p : ((x != x) ? x : 0.0);
+    return (x < -708.0) ? 0.0 : p;
 }
 
 NS_HD double ns_flog(double x)
