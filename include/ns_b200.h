@@ -177,6 +177,16 @@ int ns_glmrob_nb(ns_ctx *ctx, const ns_params *prm, int n_samples, const int32_t
                  const int32_t *x, double *sigma, double *slope, double *pvalues, double *qvalues,
                  double *gq, int32_t *extra_rob, uint32_t *flags);
 
+/*
+ * The contour / power grid of plot_rob_nb (bin/plot_rob_nb.r:80-121): toQvalue(x, y) (:83-87) for m
+ * points (gx = DP, gy = AO) against one fitted unit (coverage, ma_count, sigma, slope as returned by
+ * glmrob.nb).  qval[g] = -10 log10 of the Holm-adjusted (p.adjust's default) tail probability of the
+ * new point among the n + 1; 0 where gy > gx.  The reference evaluates up to ~3500 such points per
+ * plotted variant, each with n + 1 tail evaluations and a sort.
+ */
+int ns_qvalue_grid(ns_ctx *ctx, double sigma, double slope, int n_samples, const int32_t *coverage,
+                   const int32_t *ma_count, int64_t m, const int32_t *gx, const int32_t *gy, double *qval);
+
 /* ---- columnar loader for the mpileup2readcounts text table ------------------------------------
  * Replaces the per-line strsplit / column gathers of bin/needlestack.r:316-329 (SNV), :461-479 (DEL),
  * :624-643 (INS).  Host code, multi-threaded; the count planes are page-locked when a CUDA device is

@@ -54,6 +54,7 @@ def load_library():
     L.ns_call_snv_device.argtypes = [vp, C.POINTER(NsParams), C.c_int, C.c_int64, vp, vp, C.POINTER(NsOut)]
     L.ns_call_units.argtypes = [vp, C.POINTER(NsParams), C.c_int, C.c_int64, vp, vp, vp, vp, vp, vp, C.c_int,
                                 C.POINTER(NsOut)]
+    L.ns_qvalue_grid.argtypes = [vp, C.c_double, C.c_double, C.c_int, vp, vp, C.c_int64, vp, vp, c_dp]
     L.ns_glmrob_nb.argtypes = [vp, C.POINTER(NsParams), C.c_int, vp, vp, c_dp, c_dp, c_dp, c_dp, c_dp, c_ip, c_up]
     L.ns_measure_fp64_peak.argtypes = [vp, c_dp]
     L.ns_table_parse.restype = vp
@@ -82,7 +83,7 @@ def load_library():
 
 EXPORTED_SYMBOLS = ("ns_abi_version", "ns_sizeof", "ns_params_glm_default", "ns_params_caller_default", "ns_create", "ns_destroy",
                     "ns_last_error", "ns_set_stream", "ns_alloc_pinned", "ns_free_pinned", "ns_get_timings",
-                    "ns_call_snv", "ns_call_snv_device", "ns_call_units", "ns_glmrob_nb", "ns_measure_fp64_peak",
+                    "ns_call_snv", "ns_call_snv_device", "ns_call_units", "ns_glmrob_nb", "ns_qvalue_grid", "ns_measure_fp64_peak",
                     "ns_table_parse", "ns_table_free", "ns_table_positions", "ns_table_samples",
                     "ns_table_counts_pinned", "ns_table_counts", "ns_table_ref", "ns_table_ref_text", "ns_table_loc",
                     "ns_table_chrom", "ns_table_n_chrom", "ns_table_chrom_name", "ns_table_indel_cov",
@@ -372,6 +373,24 @@ class Caller:
         return dict(coverage=np.asarray(x, dtype=float), ma_count=np.asarray(y, dtype=float),
                     coef=dict(sigma=sigma.value, slope=slope.value), pvalues=pv, qvalues=qv, GQ=gq,
                     extra_rob=bool(er.value), flags=fl.value)
+
+
+def _qvalue_grid(self, sigma, slope, coverage, ma_count, gx, gy):
+    """toQvalue(x, y) of plot_rob_nb.r:83-87 for the points (gx[g], gy[g]) against one fitted unit: Phred-scaled
+    Holm-adjusted tail probability of the new point among the n + 1; 0 where gy > gx."""
+    cov = np.ascontiguousarray(coverage, dtype=np.int32)
+    ma = np.ascontiguousarray(ma_count, dtype=np.int32)
+    gx = np.ascontiguousarray(gx, dtype=np.int32)
+    gy = np.ascontiguousarray(gy, dtype=np.int32)
+    if cov.shape != ma.shape or cov.ndim != 1 or gx.shape != gy.shape:
+        raise ValueError("coverage/ma_count and gx/gy must be pairs of equal-length vectors")
+    out = np.empty(gx.shape, dtype=np.float64)
+    self._check(self._L.ns_qvalue_grid(self._ctx, float(sigma), float(slope), len(cov), _ptr(cov), _ptr(ma), gx.size,
+                                       _ptr(gx.reshape(-1)), _ptr(gy.reshape(-1)), out.ctypes.data_as(c_dp)))
+    return out
+
+
+Caller.qvalue_grid = _qvalue_grid
 
 
 def glmrob_nb(y, x, device=0, **kw):

@@ -86,6 +86,7 @@ struct ns_ctx {
     DevBuf<uint8_t> in_ref[2];
     DevBuf<int32_t> in_rows[5];
     DevBuf<uint8_t> in_indel;
+    DevBuf<double> grid_out;
     cudaEvent_t ev_h2d[2], ev_free[2];
     /* per-chunk unit arrays */
     DevBuf<uint32_t> flags, iters;
@@ -237,6 +238,7 @@ void ns_destroy(ns_ctx *ctx)
     for (int i = 0; i < 5; i++)
         ctx->in_rows[i].release();
     ctx->in_indel.release();
+    ctx->grid_out.release();
     ctx->flags.release(), ctx->iters.release(), ctx->cycles.release(), ctx->sigma.release(), ctx->slope.release(), ctx->max_gq.release();
     ctx->needrow.release(), ctx->row.release(), ctx->emitflag.release(), ctx->emitidx.release();
     ctx->fit_list.release(), ctx->post_list.release(), ctx->heavy_list.release(), ctx->pre_list.release(), ctx->emit_index_out.release(), ctx->emit_unit.release();
@@ -968,6 +970,49 @@ int ns_glmrob_nb(ns_ctx *ctx, const ns_params *prm, int n, const int32_t *y, con
         *extra_rob = (fl & NS_F_EXTRA_ROB) ? 1 : 0;
     if (flags)
         *flags = fl;
+    return NS_OK;
+}
+
+int ns_qvalue_grid(ns_ctx *ctx, double sigma, double slope, int n, const int32_t *coverage, const int32_t *ma_count,
+                   int64_t m, const int32_t *gx, const int32_t *gy, double *qval)
+{
+    if (!ctx)
+        return NS_ERR_ARG;
+    if (n < 1 || m < 0 || !coverage || !ma_count || (m > 0 && (!gx || !gy || !qval)) || !(sigma > 0) || !(slope > 0)) {
+        ctx->err = "ns_qvalue_grid: bad argument (the reference draws no contours when the fit is NA)";
+        return NS_ERR_ARG;
+    }
+    if (m == 0)
+        return NS_OK;
+    CK(cudaSetDevice(ctx->device));
+    const size_t sm = (NS_RTAB + 3 * (size_t)n) * sizeof(double);
+    if (sm > 227 * 1024) {
+        ctx->err = "ns_qvalue_grid: too many samples for the on-chip working set";
+        return NS_ERR_ARG;
+    }
+    cudaError_t e;
+    if ((e = ctx->in_rows[0].reserve((size_t)n)) || (e = ctx->in_rows[1].reserve((size_t)n)) ||
+        (e = ctx->in_rows[2].reserve((size_t)m)) || (e = ctx->in_rows[3].reserve((size_t)m)) ||
+        (e = ctx->grid_out.reserve((size_t)m))) {
+        ctx->err = std::string("device allocation (q-value grid) failed: ") + cudaGetErrorString(e);
+        return NS_ERR_NOMEM;
+    }
+    cudaStream_t st = ctx->stream;
+    CK(cudaMemcpyAsync(ctx->in_rows[0].p, coverage, (size_t)n * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(ctx->in_rows[1].p, ma_count, (size_t)n * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(ctx->in_rows[2].p, gx, (size_t)m * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(ctx->in_rows[3].p, gy, (size_t)m * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    if (sm > 48 * 1024)
+        CK(cudaFuncSetAttribute(k_qgrid, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    int blocks = (int)((m + 255) / 256);
+    if (blocks > 2 * ctx->sm_count)
+        blocks = 2 * ctx->sm_count;
+    k_qgrid<<<blocks, 256, sm, st>>>(n, ctx->in_rows[0].p, ctx->in_rows[1].p, sigma, slope, m, ctx->in_rows[2].p,
+                                     ctx->in_rows[3].p, ctx->grid_out.p);
+    CK(cudaGetLastError());
+    ctx->tm.kernel_launches++;
+    CK(cudaMemcpyAsync(qval, ctx->grid_out.p, (size_t)m * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
     return NS_OK;
 }
 

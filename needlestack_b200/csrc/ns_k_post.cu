@@ -63,3 +63,54 @@ __global__ void k_qtab(double *tabN, double *tabT, int len, double sigma_normal,
         tabT[x] = (afmin >= 0) ? ns_qbinom(0.01, (double)x, afmin) : 0.0;
 }
 
+
+/* toQvalue(x, y) of plot_rob_nb.r:83-87 on a grid: the Holm-adjusted tail probability of a new point
+ * (x = DP, y = AO) added to the n fitted observations, as a Phred value.  Every CTA rebuilds the
+ * unit's ascending p-values and Holm prefix maxima in shared memory (n <= ~9000), then its threads
+ * take grid points; each point is one tail evaluation + one binary search (the reference re-sorts
+ * n+1 p-values per grid point). */
+__global__ void __launch_bounds__(256)
+k_qgrid(int n, const int32_t *cov, const int32_t *ma, double sigma, double slope, int64_t m, const int32_t *gx,
+        const int32_t *gy, double *out)
+{
+    double *rtab = ns_smem, *p = ns_smem + NS_RTAB, *srt = p + n, *hm = srt + n;
+    for (int j = threadIdx.x; j < NS_RTAB; j += blockDim.x)
+        rtab[j] = j > 0 ? 1.0 / (double)j : 0.0;
+    __syncthreads();
+    const double size = 1 / sigma;
+    for (int i = threadIdx.x; i < n; i += blockDim.x)
+        p[i] = ns_nb_pvalue((double)ma[i], size, slope * (double)cov[i], rtab, NS_RTAB);
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const double pi = p[i];
+        int rank = 0;
+        for (int j = 0; j < n; j++) {
+            const double pj = p[j];
+            rank += (pj < pi) || (pj == pi && j < i);
+        }
+        srt[rank] = pi;
+    }
+    __syncthreads();
+    if (threadIdx.x < 32) { /* hm[k] = max_{j<=k} (n+1-j) srt[j]: chunk per lane, warp scan of the chunk maxima */
+        const int lane = threadIdx.x, per = (n + 31) / 32;
+        const int b0 = lane * per < n ? lane * per : n, b1 = b0 + per < n ? b0 + per : n;
+        double loc = -INFINITY;
+        for (int k = b0; k < b1; k++)
+            loc = fmax(loc, (double)(n + 1 - k) * srt[k]);
+        double run = WarpG::excl_prefix_max(loc);
+        for (int k = b0; k < b1; k++) {
+            run = fmax(run, (double)(n + 1 - k) * srt[k]);
+            hm[k] = run;
+        }
+    }
+    __syncthreads();
+    for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < m; g += (int64_t)gridDim.x * blockDim.x) {
+        const double x = (double)gx[g], y = (double)gy[g];
+        double q = 0.0;
+        if (!(y > x)) {
+            const double pstar = ns_nb_pvalue(y, size, slope * x, rtab, NS_RTAB);
+            q = -10 * log10(ns_holm_last(pstar, srt, hm, n)) + 0.0;
+        }
+        out[g] = q;
+    }
+}

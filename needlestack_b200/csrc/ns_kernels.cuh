@@ -51,4 +51,6 @@ __global__ void k_scan_total(const int *flag, const int *excl, int n, int *total
 __global__ void k_pack(int n, int n_units, int64_t u0, int64_t emit_off, int cap, ns_unit_arrays ua,
                        ns_planes src, ns_planes dst, int64_t *emit_unit, int *emit_index_out);
 __global__ void k_qtab(double *tabN, double *tabT, int len, double sigma_normal, double afmin);
+__global__ void k_qgrid(int n, const int32_t *cov, const int32_t *ma, double sigma, double slope, int64_t m, const int32_t *gx,
+                        const int32_t *gy, double *out);
 __global__ void k_dfma(double *out, int iters, double a, double b);

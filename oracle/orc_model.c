@@ -758,3 +758,32 @@ int orc_call_snv_batch(int64_t P, int n, const uint8_t *ref, const int32_t *coun
         pthread_join(th[t], NULL);
     return 0;
 }
+
+/* toQvalue(x, y) of /root/reference/bin/plot_rob_nb.r:83-87 (the contour / power grid of
+ * plot_rob_nb, :80-121): the new point (x = DP, y = AO) is appended to the n observations, all
+ * n + 1 tail probabilities dnbinom + pnbinom(lower.tail = F) are Holm-adjusted (p.adjust's
+ * default method) and the new point's value is returned on the Phred scale; 0 when y > x. */
+int orc_plot_toqvalue(int n, const int32_t *coverage, const int32_t *ma_count, double sigma, double slope,
+                      int64_t m, const int32_t *gx, const int32_t *gy, double *qval)
+{
+    double *p = (double *)malloc(sizeof(double) * (size_t)(2 * n + 2));
+    double *q = p + n + 1;
+    if (!p)
+        return -1;
+    for (int i = 0; i < n; i++) {
+        double mu = slope * (double)coverage[i];
+        p[i] = orc_dnbinom_mu((double)ma_count[i], 1 / sigma, mu) + orc_pnbinom_mu_upper((double)ma_count[i], 1 / sigma, mu);
+    }
+    for (int64_t g = 0; g < m; g++) {
+        double x = gx[g], y = gy[g];
+        if (y > x) {
+            qval[g] = 0;
+            continue;
+        }
+        p[n] = orc_dnbinom_mu(y, 1 / sigma, slope * x) + orc_pnbinom_mu_upper(y, 1 / sigma, slope * x);
+        orc_padjust_holm(n + 1, p, q);
+        qval[g] = -10 * log10(q[n]);
+    }
+    free(p);
+    return 0;
+}

@@ -87,6 +87,10 @@ int orc_call_snv_batch(int64_t P, int n, const uint8_t *ref, const int32_t *coun
                        double *gq, double *qval_minaf, double *sor, double *rvsb, double *fs,
                        uint8_t *gt, uint8_t *status, orc_unit_info *info);
 
+/* toQvalue(x, y) of plot_rob_nb.r:83-87 for m grid points against one fitted unit */
+int orc_plot_toqvalue(int n, const int32_t *coverage, const int32_t *ma_count, double sigma, double slope,
+                      int64_t m, const int32_t *gx, const int32_t *gy, double *qval);
+
 #ifdef __cplusplus
 }
 #endif

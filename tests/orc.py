@@ -92,6 +92,7 @@ def lib():
                                 c_dp, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp, c_bp, c_bp, C.POINTER(UnitInfo)]
     L.orc_call_snv_batch.argtypes = [C.c_int64, C.c_int, c_bp, c_ip, C.POINTER(CallParams), C.c_int,
                                      c_dp, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp, c_bp, c_bp, C.POINTER(UnitInfo)]
+    L.orc_plot_toqvalue.argtypes = [C.c_int, c_ip, c_ip, d, d, C.c_int64, c_ip, c_ip, c_dp]
     _LIB = L
     return L
 
@@ -199,4 +200,15 @@ def call_snv_batch(ref, counts, prm, n_threads=1):
     out["n_quad"] = np.array([info[u].glm.n_quad for u in range(U)], dtype=np.int64)
     out["pooled"] = np.array([list(info[u].pooled) for u in range(U)])
     out["info"] = info
+    return out
+
+
+def plot_toqvalue(coverage, ma_count, sigma, slope, gx, gy):
+    """toQvalue(x, y) of plot_rob_nb.r:83-87 for every (gx[g], gy[g])"""
+    cov = np.ascontiguousarray(coverage, dtype=np.int32)
+    ma = np.ascontiguousarray(ma_count, dtype=np.int32)
+    gx = np.ascontiguousarray(gx, dtype=np.int32).reshape(-1)
+    gy = np.ascontiguousarray(gy, dtype=np.int32).reshape(-1)
+    out = np.empty(len(gx))
+    lib().orc_plot_toqvalue(len(cov), _ip(cov), _ip(ma), float(sigma), float(slope), len(gx), _ip(gx), _ip(gy), _dp(out))
     return out
