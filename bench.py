@@ -339,8 +339,17 @@ def main():
     gate_s = tm_sum["gate_ms"] * 1e-3
     gate_bytes = a.steps * (P * (36.0 * n + 1) + 3 * P * 44.0)
     gate_ach = gate_bytes / gate_s / 1e9 if gate_s > 0 else 0.0
+    # DRAM bytes per launch from the committed ncu capture of this same workload (profiles/capture.sh step 3)
+    traffic = {}
+    if a.config == "C2" and P == cfg.P and n == cfg.n:
+        try:
+            tj = sorted(f for f in os.listdir(os.path.join(ROOT, "profiles")) if f.startswith("traffic_r"))[-1]
+            for k, v in json.load(open(os.path.join(ROOT, "profiles", tj)))["kernels"].items():
+                traffic[k] = v["dram_bytes_per_launch"]
+        except Exception:
+            traffic = {}
     roofline = {"kernel": "k_fit", "bound": "fp64", "achieved": ach, "peak": fp64_peak, "unit": "TFLOP/s",
-                "frac": ach / fp64_peak if fp64_peak else None, "traffic": None,
+                "frac": ach / fp64_peak if fp64_peak else None, "traffic": traffic.get("k_fit"),
                 "peak_source": "DFMA micro-benchmark run in this process (MEASURED_PEAKS.json has no FP64 entry)",
                 "flops_model": "400*N_seed + 32*N_lattice (+ 2000*N_quad, zero in this kernel) (SURVEY.md 8d); "
                                "counters from the kernel",
@@ -348,7 +357,9 @@ def main():
                                                                        "n_quad": quad},
                 "share_of_step": tm_sum["fit_ms"] / ms if ms else None}
     roofline_gate = {"kernel": "k_gate", "bound": "hbm", "achieved": gate_ach, "peak": hbm_peak, "unit": "GB/s",
-                     "frac": gate_ach / hbm_peak, "traffic": None, "peak_source": hbm_src,
+                     "frac": gate_ach / hbm_peak, "traffic": traffic.get("k_gate"), "peak_source": hbm_src,
+                     "algorithmic_bytes_per_launch": gate_bytes / (a.steps * -(-P // 262144)),
+                     "launches_per_step": -(-P // 262144),
                      "bytes_model": "36*n+1 B read per position + 44 B written per unit",
                      "share_of_step": tm_sum["gate_ms"] / ms if ms else None}
 

@@ -709,8 +709,16 @@ static int64_t ns_pick_chunk(ns_ctx *ctx, int n, int64_t total_units)
         return ctx->chunk_units;
     /* bound the per-chunk result planes (58 B per sample per row) to ~1.5 GB */
     int64_t c = (int64_t)(6000.0e6 / (58.0 * n));
-    if (c > 3 * 262144)
-        c = 3 * 262144;
+    /* ~1 GB of count planes per chunk, at least 262144 positions: small panels (WGS-like, few samples) get
+     * proportionally more positions per chunk, so that the few cluster-path units of a chunk (whose critical
+     * path is tens of ms whatever the chunk holds) are amortised over more streamed positions */
+    int64_t cap = 3 * (int64_t)(1.0e9 / (36.0 * n));
+    if (cap < 3 * 262144)
+        cap = 3 * 262144;
+    if (cap > 3 * 2097152)
+        cap = 3 * 2097152; /* per-unit arrays: ~70 B per unit */
+    if (c > cap)
+        c = cap;
     if (c < 3 * 256)
         c = 3 * 256;
     c -= c % 3;
