@@ -557,7 +557,7 @@ static int ns_run_chunk(ns_ctx *ctx, const ns_params &dprm, const double *qtab, 
     if (n_light > 0) {
         const int wpb = 4;
         size_t per_warp = ns_work_doubles(n) * sizeof(double);
-        size_t sm = NS_RTAB * sizeof(double) + wpb * per_warp;
+        size_t sm = (NS_RTAB + 256) * sizeof(double) + wpb * per_warp; /* 1/j table, log table, the warps' slices */
         if (sm > 227 * 1024) {
             ctx->err = "too many samples for the on-chip working set (n > ~1100)";
             return NS_ERR_ARG;
@@ -712,7 +712,7 @@ static int64_t ns_pick_chunk(ns_ctx *ctx, int n, int64_t total_units)
     /* ~1 GB of count planes per chunk, at least 262144 positions: small panels (WGS-like, few samples) get
      * proportionally more positions per chunk, so that the few cluster-path units of a chunk (whose critical
      * path is tens of ms whatever the chunk holds) are amortised over more streamed positions */
-    int64_t cap = 3 * (int64_t)(1.0e9 / (36.0 * n));
+    int64_t cap = 3 * (int64_t)(0.94e9 / (36.0 * n)); /* n = 100: 262144 positions, the measured end-to-end optimum */
     if (cap < 3 * 262144)
         cap = 3 * 262144;
     if (cap > 3 * 2097152)

@@ -265,11 +265,13 @@ struct ns_work {
     double *dtab;                 /* NS_JTAB: 1/(j+1/sig), the increments of digamma(j+1/sig) for the current sigma */
     double *r2tab;                /* NS_JTAB: (j+1/sig)/(j+1) for the current sigma (pmf ratio without mu/(mu+size)) */
     const double *rtab;           /* NS_RTAB: 1/j (shared by the CTA) */
+    const double *ltab;           /* MODE 1: the table of ns_flog_tab (shared by the CTA) */
     ns_coop_scratch coop;         /* MODE 2 only: this warp's spline arrays */
 };
 NS_HD size_t ns_work_doubles(int n) { return (size_t)6 * (size_t)n + 8 + 2 * NS_JTAB; }
-NS_HD void ns_work_bind(ns_work &w, double *base, int n, const double *rtab)
+NS_HD void ns_work_bind(ns_work &w, double *base, int n, const double *rtab, const double *ltab = nullptr)
 {
+    w.ltab = ltab;
     w.y = base;
     w.x = base + n;
     w.X = base + 2 * (size_t)n;
@@ -333,7 +335,8 @@ struct ns_fseed {
 };
 /* quantities shared by ai.sig.tukey and E.tukeypsi.1/.2 on a window that starts at 0:
  * sd = sqrt(V), isd = 1/sd, pm = dnbinom(0) = (1+sig mu)^(-1/sig), t_j = t0 + j*ics */
-NS_HD void ns_fast_seed(ns_fseed &S, bool valid, double sig, double invsig, double c, double inv_c, double &lg)
+NS_HD void ns_fast_seed(ns_fseed &S, bool valid, double sig, double invsig, double c, double inv_c, const double *ltab,
+                        double &lg)
 {
     S.s1 = fma(sig, S.mu, 1.0);
     ns_fsqrt2(S.mu * S.s1, S.sd, S.isd);
@@ -342,7 +345,7 @@ NS_HD void ns_fast_seed(ns_fseed &S, bool valid, double sig, double invsig, doub
     const bool shape = (lo <= 0.0) && (hi < (double)NS_JTAB); /* j1 == 0 and j2 < NS_JTAB */
     S.slow = valid && !shape;
     S.J2 = (valid && shape) ? ns_d2i_floor(hi) : -1;
-    lg = ns_flog(S.s1);
+    lg = ns_flog_tab(S.s1, ltab); /* s1 = 1 + sig mu >= 1 */
     S.pm = ns_fexp_bf(-invsig * lg);
     S.ics = S.isd * inv_c;
     S.t0 = -S.mu * S.ics;
@@ -416,7 +419,7 @@ NS_GFN double ns_sig_objective(double sig, const ns_work &w, int n, const ns_par
         double dg0 = 0;
         int have_dg0 = 0;
         const double twon = (double)(2 * prm.n_ai_sig_tukey);
-        const double inv_c = 1.0 / c;
+        const double inv_c = ns_frcp(c);
         const ns_sptr s_x(w.x), s_mu(w.mu), s_y(w.y), s_dtab(w.dtab), s_r2(w.r2tab);
         unsigned n_seed = 0, n_lat = 0; /* kept in registers, added to cnt once */
         const int nl = G::nl();
@@ -430,8 +433,8 @@ NS_GFN double ns_sig_objective(double sig, const ns_work &w, int n, const ns_par
             B.mu = vB ? s_mu[iB] : 1.0;
             B.y = vB ? s_y[iB] : 0.0;
             double lgA, lgB;
-            ns_fast_seed(A, vA, sig, invsig, c, inv_c, lgA);
-            ns_fast_seed(B, vB, sig, invsig, c, inv_c, lgB);
+            ns_fast_seed(A, vA, sig, invsig, c, inv_c, w.ltab, lgA);
+            ns_fast_seed(B, vB, sig, invsig, c, inv_c, w.ltab, lgB);
             /* window {0..J2}: everything by recurrence, no division inside the loop.
              * t_j = (j-mu)/(c sd) = t0 + j/(c sd);  psi_j = D_j - lg - (j-mu)/(mu+1/sig) = D_j + C0 - j/(mu+1/sig),
              * 1/(mu+1/sig) = sig/(1+sig mu) = sig mu / V */
@@ -630,7 +633,7 @@ NS_GFN double ns_irls_step(double sig, const ns_work &w, int n, double maxmu, co
     if (MODE == 1) {
         /* two samples per lane in flight (see ns_fast_seed).  With y1 = 1/sqrt(V): 1/(V sqrt V) = y1^3,
          * mu/(mu+1/sig) = sig mu^2 y1^2, V/mu = 1 + sig mu */
-        const double inv_c = 1.0 / c;
+        const double inv_c = ns_frcp(c);
         const int nl = G::nl();
         for (int iA = lane; iA < n; iA += 2 * nl) {
             const int iB = (iA + nl < n) ? iA + nl : iA;
@@ -641,8 +644,8 @@ NS_GFN double ns_irls_step(double sig, const ns_work &w, int n, double maxmu, co
             B.mu = vB ? s_mu[iB] : 1.0;
             B.y = vB ? s_y[iB] : 0.0;
             double lgA, lgB;
-            ns_fast_seed(A, vA, sig, invsig, c, inv_c, lgA);
-            ns_fast_seed(B, vB, sig, invsig, c, inv_c, lgB);
+            ns_fast_seed(A, vA, sig, invsig, c, inv_c, w.ltab, lgA);
+            ns_fast_seed(B, vB, sig, invsig, c, inv_c, w.ltab, lgB);
             const double qA = (sig * A.mu * A.mu) * (A.isd * A.isd), qB = (sig * B.mu * B.mu) * (B.isd * B.isd);
             double pmA = A.pm, pmB = B.pm, a1A = 0, a2A = 0, a1B = 0, a2B = 0, jd = 0.0;
             const int Jm = A.J2 > B.J2 ? A.J2 : B.J2;

@@ -48,10 +48,12 @@ k_fit(ns_unit_src src, const __grid_constant__ ns_params prm, int64_t u0, ns_uni
 {
     const int n = src.n;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    double *rtab = ns_smem;
+    double *rtab = ns_smem, *ltab = ns_smem + NS_RTAB;
+    for (int j = threadIdx.x; j < 256; j += blockDim.x)
+        ltab[j] = ns_g_logtab[j];
     ns_fill_rtab(rtab);
     ns_work w;
-    ns_work_bind(w, ns_smem + NS_RTAB + (size_t)warp * ns_work_doubles(n), n, rtab);
+    ns_work_bind(w, ns_smem + NS_RTAB + 256 + (size_t)warp * ns_work_doubles(n), n, rtab, ltab);
     unsigned long long tot_seed = 0, tot_lat = 0;
     const int n_fit = cnt->n_light;
     for (;;) {

@@ -228,6 +228,50 @@ NS_HD double ns_flog(double x)
     return dk * 6.93147180369123816490e-01 - ((hfsq - fma(s, hfsq + R, dk * 1.90821492927058770002e-10)) - f);
 }
 
+/* log(x) for x >= 1 (normal) from a 128-entry table: x = 2^k m, entry i = top 7 mantissa bits holds
+ * rc ~ 1/c_i (c_i the interval centre, c_0 = 1) and L = -log(rc); r = m*rc - 1 is one FMA with |r| < 2^-7 and
+ * log(x) = k ln2 + L + log1p(r), log1p by its Taylor series to r^8 (truncation below 2^-59 relative to r).  All
+ * terms are non-negative for x >= 1 (no cancellation; x -> 1 gives k = 0, L = 0 and the series alone).  Half the
+ * instructions of ns_flog: no reciprocal, a shorter polynomial.  The table lives in shared memory on the device
+ * (lanes index it divergently, which constant memory would serialise). */
+#include "ns_logtab.h"
+#define NS_LOG1PC_INIT {-1.0 / 8, 1.0 / 7, -1.0 / 6, 1.0 / 5, -1.0 / 4, 1.0 / 3, -0.5}
+#if defined(__CUDACC__)
+static __device__ const double ns_g_logtab[256] = NS_LOGTAB_INIT;
+static __constant__ double ns_d_log1pc[7] = NS_LOG1PC_INIT;
+#endif
+static const double ns_h_logtab[256] = NS_LOGTAB_INIT;
+static const double ns_h_log1pc[7] = NS_LOG1PC_INIT;
+
+NS_HD double ns_flog_tab(double x, const double *tab)
+{
+    long long xb;
+    memcpy(&xb, &x, sizeof xb);
+    const int hi = (int)(xb >> 32);
+    const int k = (hi >> 20) - 1023;
+    const int i = (hi >> 13) & 127;
+    const long long mb = (xb & 0x000fffffffffffffLL) | 0x3ff0000000000000LL;
+    double m;
+    memcpy(&m, &mb, sizeof m);
+    double rc, L;
+#if defined(__CUDA_ARCH__)
+    asm("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(rc), "=d"(L) : "r"((unsigned)__cvta_generic_to_shared(tab) + 16u * (unsigned)i));
+#else
+    rc = tab[2 * i];
+    L = tab[2 * i + 1];
+#endif
+    const double r = fma(m, rc, -1.0);
+    double p = fma(r, NS_TBL(log1pc)[0], NS_TBL(log1pc)[1]);
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int j = 2; j < 7; j++)
+        p = fma(p, r, NS_TBL(log1pc)[j]);
+    const double l1 = fma(r * r, p, r);
+    const double dk = (double)k;
+    return fma(dk, 6.93147180369123816490e-01, L) + fma(dk, 1.90821492927058770002e-10, l1);
+}
+
 /* ---------------------------------------------------------------------------------
  * Loader's saddle-point building blocks (R nmath stirlerr / bd0 / dbinom_raw), the
  * arithmetic behind every dnbinom() of glm_rob_nb.r:117,121,133,137,153,157,221.

@@ -19,7 +19,7 @@ def build():
     src = os.path.join(_HERE, "emul", "ns_emul.cpp")
     out = os.path.join(_HERE, "emul", "libnsemul.so")
     deps = [src] + [os.path.join(ROOT, "needlestack_b200", "csrc", f) for f in
-                    ("ns_math.cuh", "ns_quad.cuh", "ns_core.cuh", "ns_fit.cuh")] + [os.path.join(ROOT, "include", "ns_b200.h")]
+                    ("ns_math.cuh", "ns_quad.cuh", "ns_core.cuh", "ns_fit.cuh", "ns_logtab.h")] + [os.path.join(ROOT, "include", "ns_b200.h")]
     if (not os.path.exists(out)) or any(os.path.getmtime(d) > os.path.getmtime(out) for d in deps):
         subprocess.run(["g++", "-O2", "-fPIC", "-shared", "-std=c++17", "-o", out, src], check=True)
     return out
@@ -30,7 +30,7 @@ def lib():
     if _LIB is None:
         L = C.CDLL(build())
         d = C.c_double
-        for name, nargs in (("emul_dnbinom_mu", 3), ("emul_nb_pvalue", 3), ("emul_digamma", 1), ("emul_fexp", 1), ("emul_flog", 1),
+        for name, nargs in (("emul_dnbinom_mu", 3), ("emul_nb_pvalue", 3), ("emul_digamma", 1), ("emul_fexp", 1), ("emul_flog", 1), ("emul_flog_tab", 1), ("emul_fexp_bf", 1),
                             ("emul_qnbinom_mu", 3), ("emul_qbinom", 3), ("emul_fisher", 4)):
             f = getattr(L, name)
             f.restype = d

@@ -34,7 +34,7 @@ int emul_unit(int n, const int32_t *dp, const int32_t *vp, const int32_t *vm, co
     for (int j = 1; j < NS_RTAB; j++)
         rtab[j] = 1.0 / (double)j;
     ns_work w;
-    ns_work_bind(w, buf.data(), n, rtab);
+    ns_work_bind(w, buf.data(), n, rtab, ns_h_logtab);
     uint32_t flags = ns_gate_unit<SerialG>(r, n, prm, plain, w.scratch);
     *sigma = NAN;
     *slope = NAN;
@@ -90,6 +90,8 @@ double emul_nb_pvalue(double y, double size, double mu) { return ns_nb_pvalue(y,
 double emul_digamma(double x) { return ns_digamma(x); }
 double emul_fexp(double x) { return ns_fexp(x); }
 double emul_flog(double x) { return ns_flog(x); }
+double emul_flog_tab(double x) { return ns_flog_tab(x, ns_h_logtab); }
+double emul_fexp_bf(double x) { return ns_fexp_bf(x); }
 double emul_qnbinom_mu(double p, double size, double mu) { return ns_qnbinom_mu(p, size, mu); }
 double emul_qbinom(double p, double n, double pr) { return ns_qbinom(p, n, pr); }
 double emul_fisher(double a, double b, double c, double d) { return ns_fisher_2x2(a, b, c, d); }
