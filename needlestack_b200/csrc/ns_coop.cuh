@@ -27,6 +27,7 @@ struct ns_cspline {
     const double *y, *c;
     const double *rt;
     int rtn;
+    const double *b, *d; /* per-interval first / third order coefficients (ns_cspline_coefs) */
 };
 
 /* 1/d for an integer-valued d > 0: table when it reaches, division otherwise */
@@ -187,6 +188,29 @@ __device__ __forceinline__ void ns_cspline_solve(const ns_cpiv &P, const ns_coop
     }
 }
 
+/* b_i and d_i of R's spline coefficients (c_i as natural_spline() leaves it) for every interval, once per solve: the ~6 x 21 evaluations of a dqags call then cost two knot
+ * positions, four shared loads and a Horner form instead of re-deriving the coefficients each time.  Row n-1 is
+ * the linear continuation R uses to the right of the last knot (the integral runs to j2 + 1). */
+__device__ __forceinline__ void ns_cspline_coefs(const ns_coop_scratch &sc, int n, double j1, double j2, double by)
+{
+    const int lane = threadIdx.x & 31;
+    for (int i = lane; i < n; i += 32) {
+        const double xi = ns_cknot(j1, j2, by, n, i);
+        if (i < n - 1) {
+            const double di = ns_cknot(j1, j2, by, n, i + 1) - xi;
+            const double idi = ns_rcp_int(sc.rt, sc.rtn, di);
+            const double c0 = sc.c[i], c1 = sc.c[i + 1];
+            sc.ib[i] = (sc.y[i + 1] - sc.y[i]) * idi - di * (c1 + 2.0 * c0);
+            sc.m[i] = (c1 - c0) * idi;
+        } else {
+            const double dl = xi - ns_cknot(j1, j2, by, n, n - 2);
+            sc.ib[i] = (sc.y[n - 1] - sc.y[n - 2]) * ns_rcp_int(sc.rt, sc.rtn, dl) + dl * sc.c[n - 2];
+            sc.m[i] = 0.0;
+        }
+    }
+    __syncwarp();
+}
+
 __device__ __forceinline__ double ns_cspline_eval(const ns_cspline &s, double u)
 {
     const int n = s.n;
@@ -195,23 +219,21 @@ __device__ __forceinline__ double ns_cspline_eval(const ns_cspline &s, double u)
         i = 0;
     if (i > n - 1)
         i = n - 1;
-    while (i > 0 && u < ns_cknot(s.j1, s.j2, s.by, n, i))
-        i--;
-    while (i < n - 1 && u >= ns_cknot(s.j1, s.j2, s.by, n, i + 1))
-        i++;
     double xi = ns_cknot(s.j1, s.j2, s.by, n, i);
-    double dx = u - xi;
-    if (i == n - 1) {
-        double dl = xi - ns_cknot(s.j1, s.j2, s.by, n, n - 2);
-        double bl = (s.y[n - 1] - s.y[n - 2]) * ns_rcp_int(s.rt, s.rtn, dl) + dl * s.c[n - 2];
-        return s.y[i] + dx * bl;
+    while (i > 0 && u < xi) {
+        i--;
+        xi = ns_cknot(s.j1, s.j2, s.by, n, i);
     }
-    double di = ns_cknot(s.j1, s.j2, s.by, n, i + 1) - xi;
-    double idi = ns_rcp_int(s.rt, s.rtn, di);
-    double c0 = s.c[i], c1 = s.c[i + 1];
-    double b = (s.y[i + 1] - s.y[i]) * idi - di * (c1 + 2.0 * c0);
-    double d = (c1 - c0) * idi;
-    return s.y[i] + dx * (b + dx * (3.0 * c0 + dx * d));
+    while (i < n - 1) {
+        const double xn = ns_cknot(s.j1, s.j2, s.by, n, i + 1);
+        if (u < xn)
+            break;
+        i++;
+        xi = xn;
+    }
+    const double dx = u - xi;
+    const double c3 = (i == n - 1) ? 0.0 : 3.0 * s.c[i];
+    return s.y[i] + dx * (s.b[i] + dx * (c3 + dx * s.d[i]));
 }
 
 __device__ __forceinline__ double ns_wsum(double v)
@@ -274,9 +296,14 @@ struct ns_k21_coop {
         const double wk = ns_lane_wk[lane], wgw = ns_lane_wg[lane];
         if (lane < 21)
             fv = f(centr + hlgth * ns_lane_sx[lane]);
-        double resk = ns_wsum(wk * fv);
-        double resg = ns_wsum(wgw * fv);
-        double rabs = ns_wsum(wk * fabs(fv));
+        /* three independent butterflies interleaved: one shuffle latency chain instead of three */
+        double resk = wk * fv, resg = wgw * fv, rabs = wk * fabs(fv);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            resk += __shfl_xor_sync(0xffffffffu, resk, o);
+            resg += __shfl_xor_sync(0xffffffffu, resg, o);
+            rabs += __shfl_xor_sync(0xffffffffu, rabs, o);
+        }
         double reskh = resk * .5;
         double rasc = ns_wsum(lane < 21 ? wk * fabs(fv - reskh) : 0.0);
         result = resk * hlgth;
@@ -401,7 +428,8 @@ static __device__ __noinline__ double ns_ai_coop(double mui, double sig, double 
         ns_cspline_solve(P, sc, n_ai);
     }
     __syncwarp();
-    ns_cspline s = {n_ai, j1, j2, by, 1.0 / by, sc.y, sc.c, sc.rt, sc.rtn};
+    ns_cspline_coefs(sc, n_ai, j1, j2, by);
+    ns_cspline s = {n_ai, j1, j2, by, 1.0 / by, sc.y, sc.c, sc.rt, sc.rtn, sc.ib, sc.m};
     int ier = 0, np = 0;
     double v = ns_cintegrate(s, ier, np);
     cnt.n_quad += (unsigned long long)np;
@@ -489,7 +517,8 @@ static __device__ __noinline__ void ns_E12_coop(double mui, double sig, double c
     ns_cspline_pivots(P, n_ai, j1, j2, by);
     ns_cspline_solve(P, sc, n_ai);
     __syncwarp();
-    ns_cspline s = {n_ai, j1, j2, by, 1.0 / by, sc.y, sc.c, sc.rt, sc.rtn};
+    ns_cspline_coefs(sc, n_ai, j1, j2, by);
+    ns_cspline s = {n_ai, j1, j2, by, 1.0 / by, sc.y, sc.c, sc.rt, sc.rtn, sc.ib, sc.m};
     int ier1 = 0, ier2 = 0, np = 0;
     double v1 = ns_cintegrate(s, ier1, np);
     __syncwarp();
@@ -498,6 +527,7 @@ static __device__ __noinline__ void ns_E12_coop(double mui, double sig, double c
     __syncwarp();
     ns_cspline_solve(P, sc, n_ai);
     __syncwarp();
+    ns_cspline_coefs(sc, n_ai, j1, j2, by);
     double v2 = ns_cintegrate(s, ier2, np);
     cnt.n_quad += (unsigned long long)np;
     if (ier1 == 7 || ier2 == 7)
