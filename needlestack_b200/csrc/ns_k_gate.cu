@@ -296,6 +296,140 @@ __device__ __forceinline__ int ns_gate_position_reg(const ns_unit_src &src, cons
     return packed;
 }
 
+/* The streaming form of the gate (n a multiple of VEC, n <= 32 * VEC, 16- or 8-byte aligned planes):
+ *   - lane l owns samples VEC*l .. VEC*l+VEC-1: nine 128-bit (VEC = 4) or 64-bit (VEC = 2) loads per lane cover the
+ *     position, all in flight before the first use (the scalar form issued 36 loads and their address arithmetic);
+ *   - min_coverage is compared as an integer (for integer x: x > mc <=> x > floor(mc), x < mc <=> x < ceil(mc));
+ *   - the per-base statistics are reduced once with REDUX and shared by the three alleles;
+ *   - lanes 0..2 decide and commit the three units of the position side by side (one copy of the decision code and
+ *     eight store instructions per position instead of three copies and twenty-four single-lane stores).
+ * ncu (profiles/): 987 -> ~430 warp instructions per position at n = 100; the kernel was issue-bound, not
+ * HBM-bound, at 1.9 TB/s. */
+template <int VEC> struct ns_ldvec;
+template <> struct ns_ldvec<4> {
+    static __device__ __forceinline__ void ld(const int32_t *p, int *v)
+    {
+        const int4 t = __ldg(reinterpret_cast<const int4 *>(p));
+        v[0] = t.x;
+        v[1] = t.y;
+        v[2] = t.z;
+        v[3] = t.w;
+    }
+};
+template <> struct ns_ldvec<2> {
+    static __device__ __forceinline__ void ld(const int32_t *p, int *v)
+    {
+        const int2 t = __ldg(reinterpret_cast<const int2 *>(p));
+        v[0] = t.x;
+        v[1] = t.y;
+    }
+};
+
+template <int VEC>
+__device__ __forceinline__ int ns_gate_position_vec(const ns_unit_src &src, const ns_params &prm, int t_gt, int t_lt,
+                                                    int64_t p, int u_first, int n_units, const ns_unit_arrays &ua)
+{
+    const int n = src.n, lane = threadIdx.x & 31;
+    const unsigned FULL = 0xffffffffu;
+    const bool act = VEC * lane < n;
+    const int32_t *base = src.counts + p * 9 * (int64_t)n + VEC * lane;
+    int v[9][VEC];
+#pragma unroll
+    for (int r = 0; r < 9; r++) {
+#pragma unroll
+        for (int j = 0; j < VEC; j++)
+            v[r][j] = 0;
+        if (act)
+            ns_ldvec<VEC>::ld(base + (int64_t)r * n, v[r]);
+    }
+    const int ref = src.ref[p];
+    if (ref > 3) {
+        if (lane < 3 && u_first + lane < n_units)
+            ns_gate_commit(ua, prm, u_first + lane, NS_F_SKIPPED | NS_F_GATED, 0, 0.0, true);
+        return 0;
+    }
+    int n_cov = 0, n_less = 0, max_less = -1, min_geq = 0x7fffffff, maxx = 0;
+    unsigned sx = 0; /* only feeds the cluster-path prediction: a wrapped sum (depths > 2^30) costs efficiency, not results */
+#pragma unroll
+    for (int j = 0; j < VEC; j++) {
+        const int x = v[0][j];
+        n_cov += x > t_gt;
+        const bool less = x < t_lt;
+        n_less += less;
+        max_less = less ? max(max_less, x) : max_less;
+        min_geq = less ? min_geq : min(min_geq, x);
+        maxx = max(maxx, x);
+        sx += (unsigned)x;
+    }
+    if (!act) { /* the zeros of a lane beyond n are not samples */
+        n_cov = 0;
+        n_less = 0;
+        max_less = -1;
+        min_geq = 0x7fffffff;
+    }
+    int cinv[4], npos[4], mx[4], afok[4];
+    unsigned sy[4];
+#pragma unroll
+    for (int b = 0; b < 4; b++) {
+        cinv[b] = npos[b] = mx[b] = afok[b] = 0;
+        sy[b] = 0;
+#pragma unroll
+        for (int j = 0; j < VEC; j++) {
+            const int x = v[0][j], y = v[1 + b][j] + v[5 + b][j];
+            /* y/x > 0.8 (needlestack.r:330) exactly: 5y > 4x (see ns_gate_position_reg); 0/0 and lanes beyond n: false */
+            cinv[b] += 5LL * (long long)y > 4LL * (long long)x;
+            npos[b] += min(y, 1);
+            mx[b] = max(mx[b], y);
+            sy[b] += (unsigned)y;
+            if (prm.min_af > 0)
+                afok[b] |= ns_ratio_ge(y, x, prm.min_af);
+        }
+    }
+    n_cov = __reduce_add_sync(FULL, n_cov);
+    n_less = __reduce_add_sync(FULL, n_less);
+    max_less = __reduce_max_sync(FULL, max_less);
+    min_geq = __reduce_min_sync(FULL, min_geq);
+    maxx = __reduce_max_sync(FULL, maxx);
+    sx = __reduce_add_sync(FULL, sx);
+#pragma unroll
+    for (int b = 0; b < 4; b++) {
+        cinv[b] = __reduce_add_sync(FULL, cinv[b]);
+        npos[b] = __reduce_add_sync(FULL, npos[b]);
+        mx[b] = __reduce_max_sync(FULL, mx[b]);
+        sy[b] = __reduce_add_sync(FULL, sy[b]);
+        if (prm.min_af > 0)
+            afok[b] = __any_sync(FULL, afok[b]);
+    }
+    bool med_low; /* median(x) < min_coverage */
+    if (n & 1)
+        med_low = n_less >= (n + 1) / 2;
+    else if (n_less >= n / 2 + 1)
+        med_low = true;
+    else if (n_less <= n / 2 - 1)
+        med_low = false;
+    else
+        med_low = ((double)max_less + (double)min_geq) / 2 < prm.min_coverage;
+    const bool pos_gate = med_low || n_cov < prm.size_min;
+#define NS_SEL4(a, b) ((b) == 0 ? a[0] : (b) == 1 ? a[1] : (b) == 2 ? a[2] : a[3])
+    /* lane k < 3 = allele k of setdiff(c(A,T,C,G), ref) */
+    const int k = lane < 3 ? lane : 0;
+    const int alt = k + (k >= ref ? 1 : 0);
+    const bool inv = (double)NS_SEL4(cinv, alt) > 0.5 * (double)n; /* needlestack.r:330 */
+    const int yb = inv ? ref : alt;
+    const int np_ = NS_SEL4(npos, yb), maxy = NS_SEL4(mx, yb);
+    bool gate = pos_gate || (double)maxy < prm.min_reads || np_ == 0;
+    if (prm.min_af > 0)
+        gate = gate || !NS_SEL4(afok, yb);
+    const uint32_t flags = (inv ? NS_F_REF_INV : 0u) | (gate ? NS_F_GATED : 0u);
+    /* pooled allelic fraction times the largest depth: first-fit mean of the deepest sample */
+    const double mu_hint = (!gate && sx > 0) ? 1.1 * (double)NS_SEL4(sy, yb) / (double)sx * (double)maxx : 0.0;
+#undef NS_SEL4
+    const bool writer = lane < 3 && u_first + lane < n_units;
+    int cls = ns_gate_commit(ua, prm, u_first + k, flags, 0, mu_hint, writer);
+    cls = writer ? cls << (3 * lane) : 0;
+    return (int)__reduce_or_sync(FULL, (unsigned)cls);
+}
+
 __global__ void __launch_bounds__(NS_WPB_GATE * 32, 3)
 k_gate(ns_unit_src src, ns_params prm, int64_t u0, int n_units, ns_unit_arrays ua, ns_counters *cnt)
 {
@@ -305,11 +439,22 @@ k_gate(ns_unit_src src, ns_params prm, int64_t u0, int n_units, ns_unit_arrays u
     if (src.mode == 0 && !prm.extra_rob && (u0 % 3) == 0) {
         /* fast path: warp = position (uniform trip count per CTA: the list insertion is a CTA collective) */
         const int n_pos = (n_units + 2) / 3;
+        /* integer forms of the min_coverage tests; vector loads need aligned planes */
+        const double mcv = prm.min_coverage;
+        const int t_gt = mcv < 0 ? -1 : (int)floor(mcv), t_lt = mcv <= 0 ? 0 : (int)ceil(mcv);
+        const bool small_mc = mcv < 2.0e9;
+        const uintptr_t addr = (uintptr_t)src.counts;
+        const int vec = (small_mc && (n & 3) == 0 && n > 32 && n <= 128 && (addr & 15) == 0) ? 4
+                        : (small_mc && (n & 1) == 0 && n > 16 && n <= 64 && (addr & 7) == 0) ? 2 : 0;
         for (int q0 = blockIdx.x * NS_WPB_GATE; q0 < n_pos; q0 += wstride) {
             const int q = q0 + warp;
             int packed = 0;
             if (q < n_pos) {
-                if (n <= 64)
+                if (vec == 4)
+                    packed = ns_gate_position_vec<4>(src, prm, t_gt, t_lt, u0 / 3 + q, 3 * q, n_units, ua);
+                else if (vec == 2)
+                    packed = ns_gate_position_vec<2>(src, prm, t_gt, t_lt, u0 / 3 + q, 3 * q, n_units, ua);
+                else if (n <= 64)
                     packed = ns_gate_position_reg<2>(src, prm, u0 / 3 + q, 3 * q, n_units, ua);
                 else if (n <= 128)
                     packed = ns_gate_position_reg<4>(src, prm, u0 / 3 + q, 3 * q, n_units, ua);
