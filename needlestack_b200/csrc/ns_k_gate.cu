@@ -348,57 +348,71 @@ __device__ __forceinline__ int ns_gate_position_vec(const ns_unit_src &src, cons
             ns_gate_commit(ua, prm, u_first + lane, NS_F_SKIPPED | NS_F_GATED, 0, 0.0, true);
         return 0;
     }
-    int n_cov = 0, n_less = 0, max_less = -1, min_geq = 0x7fffffff, maxx = 0;
+    int n_cov = 0, n_less = 0, maxx = 0;
     unsigned sx = 0; /* only feeds the cluster-path prediction: a wrapped sum (depths > 2^30) costs efficiency, not results */
 #pragma unroll
     for (int j = 0; j < VEC; j++) {
         const int x = v[0][j];
         n_cov += x > t_gt;
-        const bool less = x < t_lt;
-        n_less += less;
-        max_less = less ? max(max_less, x) : max_less;
-        min_geq = less ? min_geq : min(min_geq, x);
+        n_less += x < t_lt;
         maxx = max(maxx, x);
         sx += (unsigned)x;
     }
     if (!act) { /* the zeros of a lane beyond n are not samples */
         n_cov = 0;
         n_less = 0;
-        max_less = -1;
-        min_geq = 0x7fffffff;
     }
-    int cinv[4], npos[4], mx[4], afok[4];
+    n_cov = __reduce_add_sync(FULL, n_cov);
+    n_less = __reduce_add_sync(FULL, n_less);
+    maxx = __reduce_max_sync(FULL, maxx);
+    sx = __reduce_add_sync(FULL, sx);
+    /* per base: #(y/x > 0.8) (needlestack.r:330: exactly 5y > 4x for integers, see ns_gate_position_reg; 0/0 and the
+     * zeros of lanes beyond n are false), max(y), sum(y).  sum(y > 0) == 0 (glm_rob_nb.r:38) is max(y) == 0.
+     * Depths below 2^28 (always, in practice) keep 5y - 4x in 32 bits. */
+    int cinv[4], mx[4], afok[4];
     unsigned sy[4];
+    const bool wide = maxx >= (1 << 28);
 #pragma unroll
     for (int b = 0; b < 4; b++) {
-        cinv[b] = npos[b] = mx[b] = afok[b] = 0;
+        cinv[b] = mx[b] = afok[b] = 0;
         sy[b] = 0;
 #pragma unroll
         for (int j = 0; j < VEC; j++) {
             const int x = v[0][j], y = v[1 + b][j] + v[5 + b][j];
-            /* y/x > 0.8 (needlestack.r:330) exactly: 5y > 4x (see ns_gate_position_reg); 0/0 and lanes beyond n: false */
-            cinv[b] += 5LL * (long long)y > 4LL * (long long)x;
-            npos[b] += min(y, 1);
+            if (wide)
+                cinv[b] += 5LL * (long long)y > 4LL * (long long)x;
+            else
+                cinv[b] += (unsigned)(4 * x - 5 * y) >> 31; /* sign bit of 4x - 5y */
             mx[b] = max(mx[b], y);
             sy[b] += (unsigned)y;
-            if (prm.min_af > 0)
-                afok[b] |= ns_ratio_ge(y, x, prm.min_af);
         }
     }
-    n_cov = __reduce_add_sync(FULL, n_cov);
-    n_less = __reduce_add_sync(FULL, n_less);
-    max_less = __reduce_max_sync(FULL, max_less);
-    min_geq = __reduce_min_sync(FULL, min_geq);
-    maxx = __reduce_max_sync(FULL, maxx);
-    sx = __reduce_add_sync(FULL, sx);
+    if (prm.min_af > 0) {
+#pragma unroll
+        for (int b = 0; b < 4; b++)
+#pragma unroll
+            for (int j = 0; j < VEC; j++)
+                afok[b] |= ns_ratio_ge(v[1 + b][j] + v[5 + b][j], v[0][j], prm.min_af);
+#pragma unroll
+        for (int b = 0; b < 4; b++)
+            afok[b] = __any_sync(FULL, afok[b]);
+    }
 #pragma unroll
     for (int b = 0; b < 4; b++) {
         cinv[b] = __reduce_add_sync(FULL, cinv[b]);
-        npos[b] = __reduce_add_sync(FULL, npos[b]);
         mx[b] = __reduce_max_sync(FULL, mx[b]);
         sy[b] = __reduce_add_sync(FULL, sy[b]);
-        if (prm.min_af > 0)
-            afok[b] = __any_sync(FULL, afok[b]);
+    }
+    if (!wide && max(max(mx[0], mx[1]), max(mx[2], mx[3])) >= (1 << 28)) {
+        /* counts far above the depth (malformed input): redo the inversion test in 64 bits */
+#pragma unroll
+        for (int b = 0; b < 4; b++) {
+            int c = 0;
+#pragma unroll
+            for (int j = 0; j < VEC; j++)
+                c += 5LL * (long long)(v[1 + b][j] + v[5 + b][j]) > 4LL * (long long)v[0][j];
+            cinv[b] = __reduce_add_sync(FULL, c);
+        }
     }
     bool med_low; /* median(x) < min_coverage */
     if (n & 1)
@@ -407,8 +421,22 @@ __device__ __forceinline__ int ns_gate_position_vec(const ns_unit_src &src, cons
         med_low = true;
     else if (n_less <= n / 2 - 1)
         med_low = false;
-    else
+    else { /* the two middle order statistics straddle the threshold (rare): they are max{x < c} and min{x >= c} */
+        int max_less = -1, min_geq = 0x7fffffff;
+        if (act) {
+#pragma unroll
+            for (int j = 0; j < VEC; j++) {
+                const int x = v[0][j];
+                if (x < t_lt)
+                    max_less = max(max_less, x);
+                else
+                    min_geq = min(min_geq, x);
+            }
+        }
+        max_less = __reduce_max_sync(FULL, max_less);
+        min_geq = __reduce_min_sync(FULL, min_geq);
         med_low = ((double)max_less + (double)min_geq) / 2 < prm.min_coverage;
+    }
     const bool pos_gate = med_low || n_cov < prm.size_min;
 #define NS_SEL4(a, b) ((b) == 0 ? a[0] : (b) == 1 ? a[1] : (b) == 2 ? a[2] : a[3])
     /* lane k < 3 = allele k of setdiff(c(A,T,C,G), ref) */
@@ -416,8 +444,8 @@ __device__ __forceinline__ int ns_gate_position_vec(const ns_unit_src &src, cons
     const int alt = k + (k >= ref ? 1 : 0);
     const bool inv = (double)NS_SEL4(cinv, alt) > 0.5 * (double)n; /* needlestack.r:330 */
     const int yb = inv ? ref : alt;
-    const int np_ = NS_SEL4(npos, yb), maxy = NS_SEL4(mx, yb);
-    bool gate = pos_gate || (double)maxy < prm.min_reads || np_ == 0;
+    const int maxy = NS_SEL4(mx, yb);
+    bool gate = pos_gate || (double)maxy < prm.min_reads || maxy == 0;
     if (prm.min_af > 0)
         gate = gate || !NS_SEL4(afok, yb);
     const uint32_t flags = (inv ? NS_F_REF_INV : 0u) | (gate ? NS_F_GATED : 0u);
