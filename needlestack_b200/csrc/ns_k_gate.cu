@@ -60,11 +60,12 @@ __device__ __forceinline__ int ns_gate_commit(const ns_unit_arrays &ua, const ns
     return cls;
 }
 
-/* Appends up to three units per warp (packed classes, 3 bits per unit k = lane) to the work lists:
- * slots are reserved with shared-memory atomics inside the CTA and ONE global atomic per list per CTA
- * iteration (per-unit global atomics on three addresses were the gate kernel's bottleneck).
- * Must be called by all threads of the CTA. */
-__device__ __forceinline__ void ns_gate_insert(int packed, int u_first, int n_units, const ns_unit_arrays &ua,
+/* Appends the units of K positions per warp (packed classes, 3 bits per allele; lane = 3*j + k is allele k of the
+ * warp's j-th position, unit u_of(j) + k) to the work lists: slots are reserved with shared-memory atomics inside
+ * the CTA and ONE global atomic per list per CTA iteration (per-unit global atomics on three addresses were the
+ * gate kernel's bottleneck; K > 1 amortises the three CTA barriers).  Must be called by all threads of the CTA. */
+template <int K, class UOF>
+__device__ __forceinline__ void ns_gate_insert(const int (&packed)[K], UOF u_of, int n_units, const ns_unit_arrays &ua,
                                                ns_counters *cnt)
 {
     __shared__ int s_cnt[3], s_base[3];
@@ -72,14 +73,21 @@ __device__ __forceinline__ void ns_gate_insert(int packed, int u_first, int n_un
     if (threadIdx.x < 3)
         s_cnt[threadIdx.x] = 0;
     __syncthreads();
-    int cls = 0, off_l = 0, off_p = 0;
-    const int u = u_first + lane;
-    if (lane < 3 && u < n_units) {
-        cls = (packed >> (3 * lane)) & 7;
-        if (cls & 3)
-            off_l = atomicAdd(&s_cnt[(cls & 3) - 1], 1);
-        if (cls & 4)
-            off_p = atomicAdd(&s_cnt[2], 1);
+    int cls = 0, off_l = 0, off_p = 0, u = 0;
+    if (lane < 3 * K) {
+        const int j = lane / 3, k = lane - 3 * j;
+        int pk = packed[0];
+#pragma unroll
+        for (int t = 1; t < K; t++)
+            pk = (j == t) ? packed[t] : pk;
+        u = u_of(j) + k;
+        if (u < n_units) {
+            cls = (pk >> (3 * k)) & 7;
+            if (cls & 3)
+                off_l = atomicAdd(&s_cnt[(cls & 3) - 1], 1);
+            if (cls & 4)
+                off_p = atomicAdd(&s_cnt[2], 1);
+        }
     }
     __syncthreads();
     if (threadIdx.x < 3) {
@@ -368,7 +376,7 @@ __device__ __forceinline__ int ns_gate_position_vec(const ns_unit_src &src, cons
     sx = __reduce_add_sync(FULL, sx);
     /* per base: #(y/x > 0.8) (needlestack.r:330: exactly 5y > 4x for integers, see ns_gate_position_reg; 0/0 and the
      * zeros of lanes beyond n are false), max(y), sum(y).  sum(y > 0) == 0 (glm_rob_nb.r:38) is max(y) == 0.
-     * Depths below 2^28 (always, in practice) keep 5y - 4x in 32 bits. */
+     * Depths and counts below 2^28 (always, in practice) keep 4x - 5y in 32 bits. */
     int cinv[4], mx[4], afok[4];
     unsigned sy[4];
     const bool wide = maxx >= (1 << 28);
@@ -379,10 +387,7 @@ __device__ __forceinline__ int ns_gate_position_vec(const ns_unit_src &src, cons
 #pragma unroll
         for (int j = 0; j < VEC; j++) {
             const int x = v[0][j], y = v[1 + b][j] + v[5 + b][j];
-            if (wide)
-                cinv[b] += 5LL * (long long)y > 4LL * (long long)x;
-            else
-                cinv[b] += (unsigned)(4 * x - 5 * y) >> 31; /* sign bit of 4x - 5y */
+            cinv[b] += (unsigned)(4 * x - 5 * y) >> 31; /* sign bit of 4x - 5y; redone below when it could wrap */
             mx[b] = max(mx[b], y);
             sy[b] += (unsigned)y;
         }
@@ -403,8 +408,8 @@ __device__ __forceinline__ int ns_gate_position_vec(const ns_unit_src &src, cons
         mx[b] = __reduce_max_sync(FULL, mx[b]);
         sy[b] = __reduce_add_sync(FULL, sy[b]);
     }
-    if (!wide && max(max(mx[0], mx[1]), max(mx[2], mx[3])) >= (1 << 28)) {
-        /* counts far above the depth (malformed input): redo the inversion test in 64 bits */
+    if (wide || max(max(mx[0], mx[1]), max(mx[2], mx[3])) >= (1 << 28)) {
+        /* depths or counts of 2^28 and more (the latter only in malformed input): the inversion test in 64 bits */
 #pragma unroll
         for (int b = 0; b < 4; b++) {
             int c = 0;
@@ -474,22 +479,31 @@ k_gate(ns_unit_src src, ns_params prm, int64_t u0, int n_units, ns_unit_arrays u
         const uintptr_t addr = (uintptr_t)src.counts;
         const int vec = (small_mc && (n & 3) == 0 && n > 32 && n <= 128 && (addr & 15) == 0) ? 4
                         : (small_mc && (n & 1) == 0 && n > 16 && n <= 64 && (addr & 7) == 0) ? 2 : 0;
-        for (int q0 = blockIdx.x * NS_WPB_GATE; q0 < n_pos; q0 += wstride) {
-            const int q = q0 + warp;
-            int packed = 0;
-            if (q < n_pos) {
-                if (vec == 4)
-                    packed = ns_gate_position_vec<4>(src, prm, t_gt, t_lt, u0 / 3 + q, 3 * q, n_units, ua);
-                else if (vec == 2)
-                    packed = ns_gate_position_vec<2>(src, prm, t_gt, t_lt, u0 / 3 + q, 3 * q, n_units, ua);
-                else if (n <= 64)
-                    packed = ns_gate_position_reg<2>(src, prm, u0 / 3 + q, 3 * q, n_units, ua);
-                else if (n <= 128)
-                    packed = ns_gate_position_reg<4>(src, prm, u0 / 3 + q, 3 * q, n_units, ua);
-                else
-                    packed = ns_gate_position(src, prm, u0 / 3 + q, 3 * q, n_units, ua);
+        constexpr int K = 4; /* positions per warp between two list insertions */
+        for (int q0 = blockIdx.x * NS_WPB_GATE * K; q0 < n_pos; q0 += wstride * K) {
+            int packed[K];
+#pragma unroll 1
+            for (int j = 0; j < K; j++) {
+                const int q = q0 + j * NS_WPB_GATE + warp;
+                int pk = 0;
+                if (q < n_pos) {
+                    if (vec == 4)
+                        pk = ns_gate_position_vec<4>(src, prm, t_gt, t_lt, u0 / 3 + q, 3 * q, n_units, ua);
+                    else if (vec == 2)
+                        pk = ns_gate_position_vec<2>(src, prm, t_gt, t_lt, u0 / 3 + q, 3 * q, n_units, ua);
+                    else if (n <= 64)
+                        pk = ns_gate_position_reg<2>(src, prm, u0 / 3 + q, 3 * q, n_units, ua);
+                    else if (n <= 128)
+                        pk = ns_gate_position_reg<4>(src, prm, u0 / 3 + q, 3 * q, n_units, ua);
+                    else
+                        pk = ns_gate_position(src, prm, u0 / 3 + q, 3 * q, n_units, ua);
+                }
+#pragma unroll
+                for (int t = 0; t < K; t++)
+                    if (t == j)
+                        packed[t] = pk;
             }
-            ns_gate_insert(packed, 3 * q, n_units, ua, cnt);
+            ns_gate_insert<K>(packed, [&](int j) { return 3 * (q0 + j * NS_WPB_GATE + warp); }, n_units, ua, cnt);
         }
         return;
     }
@@ -503,7 +517,8 @@ k_gate(ns_unit_src src, ns_params prm, int64_t u0, int n_units, ns_unit_arrays u
             uint32_t flags = ns_gate_unit<WarpG>(r, n, prm, src.plain, scratch, &mu_hint);
             packed = ns_gate_commit(ua, prm, u, flags, r.is_indel, mu_hint, lane == 0);
         }
-        ns_gate_insert(packed, u, n_units, ua, cnt);
+        const int pk1[1] = {packed};
+        ns_gate_insert<1>(pk1, [&](int) { return u; }, n_units, ua, cnt);
     }
 }
 
