@@ -463,7 +463,7 @@ __device__ __forceinline__ int ns_gate_position_vec(const ns_unit_src &src, cons
     return (int)__reduce_or_sync(FULL, (unsigned)cls);
 }
 
-__global__ void __launch_bounds__(NS_WPB_GATE * 32, 3)
+__global__ void __launch_bounds__(NS_WPB_GATE * 32, 4)
 k_gate(ns_unit_src src, ns_params prm, int64_t u0, int n_units, ns_unit_arrays ua, ns_counters *cnt)
 {
     const int n = src.n;
