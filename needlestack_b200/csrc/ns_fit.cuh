@@ -484,10 +484,61 @@ NS_GFN double ns_sig_objective(double sig, const ns_work &w, int n, const ns_par
         cnt.n_lattice += n_lat;
     } else {
         const double dg0 = ns_digamma(invsig);
+        const double twon = (double)(2 * prm.n_ai_sig_tukey);
+#if defined(__CUDA_ARCH__)
+        /* throughput regime only: with few samples per warp (a unit on a full cluster) the lanes sharing one
+         * window is the shorter critical path */
+        const bool per_thread = (MODE == 2) && n >= 4 * G::nl();
+        if (per_thread) {
+            /* Windows that stay on the lattice-sum branch (<= 2 n_ai points; 94 % of the sample evaluations of a
+             * deep panel, 25 points on average) are taken one sample per THREAD, serially: with the warp's lanes
+             * sharing such a window every lane paid a pmf seed and a digamma for one or two lattice points.  The
+             * spline + quadrature windows keep the warp-per-sample form below. */
+            const int lid = threadIdx.x & 31;
+            double accA = 0;
+            int nsA = 0, nlA = 0;
+            for (int i = G::lane() * 32 + lid; i < n; i += G::nl() * 32) {
+                if (!(w.x[i] > 0))
+                    continue;
+                const double mu = w.mu[i], y = w.y[i];
+                const double sqrtV = sqrt(mu * (sig * mu + 1)); /* as in ai.sig.tukey */
+                const double j1 = fmax(ceil(mu - c * sqrtV), 0.0), j2 = floor(mu + c * sqrtV);
+                if (j2 - j1 + 1 > twon)
+                    continue;
+                const double sd = sqrt(ns_varfunc(mu, sig));
+                const double r = (y - mu) / sd;
+                const double wi = ns_tukeypsi(r, c) / r;
+                double term = 0.0;
+                if (wi != 0.0) {
+                    double psiML = ns_digamma(r * sqrt(mu * (sig * mu + 1)) + mu + 1 / sig) -
+                                   sig * r * sqrt(mu / (sig * mu + 1)) - dg0 - log(sig * mu + 1);
+                    term = wi * psiML;
+                }
+                nsA++;
+                if (!(j1 > j2)) {
+                    nlA += (int)(j2 - j1 + 1);
+                    term -= ns_ai_sum(mu, sig, c, j1, j2, dg0);
+                }
+                accA += term;
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1)
+                accA += __shfl_xor_sync(0xffffffffu, accA, o);
+            acc = accA; /* uniform in the warp, like the terms added below */
+            cnt.n_seed += (unsigned long long)__reduce_add_sync(0xffffffffu, nsA);
+            cnt.n_lattice += (unsigned long long)__reduce_add_sync(0xffffffffu, nlA);
+        }
+#endif
         for (int i = G::lane(); i < n; i += G::nl()) {
             if (!(w.x[i] > 0))
                 continue;
             double mu = w.mu[i], y = w.y[i];
+            if (MODE == 2 && n >= 4 * G::nl()) { /* only the spline windows are left */
+                const double sqrtV = sqrt(mu * (sig * mu + 1));
+                const double j1 = fmax(ceil(mu - c * sqrtV), 0.0), j2 = floor(mu + c * sqrtV);
+                if (!(j2 - j1 + 1 > twon))
+                    continue;
+            }
             double sd = sqrt(ns_varfunc(mu, sig));
             double r = (y - mu) / sd;
             double wi = ns_tukeypsi(r, c) / r; /* r == 0 -> NaN, as in R */
@@ -700,32 +751,83 @@ NS_GFN double ns_irls_step(double sig, const ns_work &w, int n, double maxmu, co
                 }
             }
         }
-    } else
-    for (int i = lane; i < n; i += G::nl()) {
-        if (!(s_x[i] > 0))
-            continue;
-        const double mu = s_mu[i], eta = s_eta[i], y = s_y[i];
-        double e1, sap;
-        const double V = ns_varfunc(mu, sig);
-        const double sV = sqrt(V);
+    } else {
 #if defined(__CUDA_ARCH__)
-        if (MODE == 2)
-            ns_E12_coop(mu, sig, c, prm.n_ai_sig_tukey, w.coop, res.cnt, &e1, &sap);
-        else
-#endif
-            ns_E_tukeypsi_12(mu, sig, c, prm.n_ai_sig_tukey, res.cnt, e1, sap);
-        double ee = exp(eta); /* derivinvlink(eta) = exp(log(mu)) */
-        double bi = sap * (1.0 / (V * sV)) * (ee * ee);
-        double ei = (ns_tukeypsi((y - mu) / sV, c) - e1) / sap * V * (1 / mu);
-        double zi = eta + ei;
-        if (bi != bi || zi != zi) {
-            nanrows++; /* lm(): na.omit drops the row */
-            continue;
+        const bool per_thread = (MODE == 2) && n >= 4 * G::nl();
+        if (per_thread) {
+            /* lattice-sum windows: one sample per thread (see ns_sig_objective) */
+            const int lid = threadIdx.x & 31;
+            double swA = 0, swzA = 0;
+            int nsA = 0, nlA = 0;
+            for (int i = G::lane() * 32 + lid; i < n; i += G::nl() * 32) {
+                if (!(s_x[i] > 0))
+                    continue;
+                const double mu = s_mu[i], eta = s_eta[i], y = s_y[i];
+                const double V = ns_varfunc(mu, sig);
+                const double sV = sqrt(V);
+                const double j1 = fmax(ceil(mu - c * sV), 0.0), j2 = floor(mu + c * sV);
+                if (j2 - j1 + 1 > twon)
+                    continue;
+                double e1 = 0, sap = 0;
+                nsA++;
+                if (!(j1 > j2)) {
+                    nlA += (int)(j2 - j1 + 1);
+                    ns_E12_sum(mu, sig, c, j1, j2, e1, sap);
+                }
+                const double ee = exp(eta);
+                const double bi = sap * (1.0 / (V * sV)) * (ee * ee);
+                const double ei = (ns_tukeypsi((y - mu) / sV, c) - e1) / sap * V * (1 / mu);
+                const double zi = eta + ei;
+                if (bi != bi || zi != zi) {
+                    nanrows++;
+                    continue;
+                }
+                if (bi == 0)
+                    continue;
+                swA += bi;
+                swzA += bi * (zi - s_X[i]);
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                swA += __shfl_xor_sync(0xffffffffu, swA, o);
+                swzA += __shfl_xor_sync(0xffffffffu, swzA, o);
+            }
+            sw = swA;
+            swz = swzA;
+            nanrows = __any_sync(0xffffffffu, nanrows);
+            n_seed += (unsigned)__reduce_add_sync(0xffffffffu, nsA);
+            n_lat += (unsigned)__reduce_add_sync(0xffffffffu, nlA);
         }
-        if (bi == 0)
-            continue; /* lm.wfit(): zero-weight rows excluded */
-        sw += bi;
-        swz += bi * (zi - s_X[i]);
+#endif
+        for (int i = lane; i < n; i += G::nl()) {
+            if (!(s_x[i] > 0))
+                continue;
+            const double mu = s_mu[i], eta = s_eta[i], y = s_y[i];
+            double e1, sap;
+            const double V = ns_varfunc(mu, sig);
+            const double sV = sqrt(V);
+#if defined(__CUDA_ARCH__)
+            if (MODE == 2) {
+                const double j1 = fmax(ceil(mu - c * sV), 0.0), j2 = floor(mu + c * sV);
+                if (per_thread && !(j2 - j1 + 1 > twon))
+                    continue; /* done above */
+                ns_E12_coop(mu, sig, c, prm.n_ai_sig_tukey, w.coop, res.cnt, &e1, &sap);
+            } else
+#endif
+                ns_E_tukeypsi_12(mu, sig, c, prm.n_ai_sig_tukey, res.cnt, e1, sap);
+            double ee = exp(eta); /* derivinvlink(eta) = exp(log(mu)) */
+            double bi = sap * (1.0 / (V * sV)) * (ee * ee);
+            double ei = (ns_tukeypsi((y - mu) / sV, c) - e1) / sap * V * (1 / mu);
+            double zi = eta + ei;
+            if (bi != bi || zi != zi) {
+                nanrows++; /* lm(): na.omit drops the row */
+                continue;
+            }
+            if (bi == 0)
+                continue; /* lm.wfit(): zero-weight rows excluded */
+            sw += bi;
+            swz += bi * (zi - s_X[i]);
+        }
     }
     res.cnt.n_seed += n_seed;
     res.cnt.n_lattice += n_lat;
