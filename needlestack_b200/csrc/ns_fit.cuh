@@ -404,6 +404,44 @@ static NS_HDN int ns_irls_slow(double mu, double sig, double c, double twon, dou
     return 1;
 }
 
+#if defined(__CUDACC__)
+/* Deferred-sample list of the cluster kernel's two-phase evaluation (per CTA, in w.scratch): threads append the
+ * samples they leave to the warp-cooperative path in any order, ns_deflist_sort() orders the list by sample index so
+ * that the assignment of samples to warps - and with it every floating-point sum - is the same in every run. */
+
+struct ns_deflist {
+    int *cnt, *raw, *srt;
+    __device__ __forceinline__ ns_deflist(double *scratch, int n)
+    {
+        cnt = reinterpret_cast<int *>(scratch);
+        raw = cnt + 2;
+        srt = raw + n;
+    }
+    __device__ __forceinline__ void reset()
+    {
+        __syncthreads();
+        if (threadIdx.x == 0)
+            cnt[0] = 0;
+        __syncthreads();
+    }
+    __device__ __forceinline__ void push(int i) { raw[atomicAdd(cnt, 1)] = i; }
+    __device__ __forceinline__ int sort()
+    {
+        __syncthreads();
+        const int L = cnt[0];
+        for (int t = threadIdx.x; t < L; t += blockDim.x) {
+            const int v = raw[t];
+            int rank = 0;
+            for (int u = 0; u < L; u++)
+                rank += raw[u] < v;
+            srt[rank] = v;
+        }
+        __syncthreads();
+        return L;
+    }
+};
+#endif
+
 /* out of line on purpose: three call sites in the Brent driver; inlining them tripled the kernel's
  * code and the warps stalled on instruction fetch (ncu: 32 % of issue stalls) */
 template <class G, int MODE>
@@ -497,14 +535,18 @@ NS_GFN double ns_sig_objective(double sig, const ns_work &w, int n, const ns_par
             const int lid = threadIdx.x & 31;
             double accA = 0;
             int nsA = 0, nlA = 0;
+            ns_deflist dl(w.scratch, n);
+            dl.reset();
             for (int i = G::lane() * 32 + lid; i < n; i += G::nl() * 32) {
                 if (!(w.x[i] > 0))
                     continue;
                 const double mu = w.mu[i], y = w.y[i];
                 const double sqrtV = sqrt(mu * (sig * mu + 1)); /* as in ai.sig.tukey */
                 const double j1 = fmax(ceil(mu - c * sqrtV), 0.0), j2 = floor(mu + c * sqrtV);
-                if (j2 - j1 + 1 > twon)
+                if (j2 - j1 + 1 > twon) {
+                    dl.push(i); /* spline windows: the lanes of a warp share them */
                     continue;
+                }
                 const double sd = sqrt(ns_varfunc(mu, sig));
                 const double r = (y - mu) / sd;
                 const double wi = ns_tukeypsi(r, c) / r;
@@ -529,16 +571,24 @@ NS_GFN double ns_sig_objective(double sig, const ns_work &w, int n, const ns_par
             cnt.n_lattice += (unsigned long long)__reduce_add_sync(0xffffffffu, nlA);
         }
 #endif
-        for (int i = G::lane(); i < n; i += G::nl()) {
+        int n_iter = n, i_first = G::lane(), i_step = G::nl();
+#if defined(__CUDA_ARCH__)
+        ns_deflist dl(w.scratch, n);
+        if (per_thread) { /* the deferred samples of this CTA, dealt to its warps in index order */
+            n_iter = dl.sort();
+            i_first = G::llane();
+            i_step = G::lnl();
+        }
+#endif
+        for (int it = i_first; it < n_iter; it += i_step) {
+            int i = it;
+#if defined(__CUDA_ARCH__)
+            if (per_thread)
+                i = dl.srt[it];
+#endif
             if (!(w.x[i] > 0))
                 continue;
             double mu = w.mu[i], y = w.y[i];
-            if (MODE == 2 && n >= 4 * G::nl()) { /* only the spline windows are left */
-                const double sqrtV = sqrt(mu * (sig * mu + 1));
-                const double j1 = fmax(ceil(mu - c * sqrtV), 0.0), j2 = floor(mu + c * sqrtV);
-                if (!(j2 - j1 + 1 > twon))
-                    continue;
-            }
             double sd = sqrt(ns_varfunc(mu, sig));
             double r = (y - mu) / sd;
             double wi = ns_tukeypsi(r, c) / r; /* r == 0 -> NaN, as in R */
@@ -759,6 +809,8 @@ NS_GFN double ns_irls_step(double sig, const ns_work &w, int n, double maxmu, co
             const int lid = threadIdx.x & 31;
             double swA = 0, swzA = 0;
             int nsA = 0, nlA = 0;
+            ns_deflist dl(w.scratch, n);
+            dl.reset();
             for (int i = G::lane() * 32 + lid; i < n; i += G::nl() * 32) {
                 if (!(s_x[i] > 0))
                     continue;
@@ -766,8 +818,10 @@ NS_GFN double ns_irls_step(double sig, const ns_work &w, int n, double maxmu, co
                 const double V = ns_varfunc(mu, sig);
                 const double sV = sqrt(V);
                 const double j1 = fmax(ceil(mu - c * sV), 0.0), j2 = floor(mu + c * sV);
-                if (j2 - j1 + 1 > twon)
+                if (j2 - j1 + 1 > twon) {
+                    dl.push(i);
                     continue;
+                }
                 double e1 = 0, sap = 0;
                 nsA++;
                 if (!(j1 > j2)) {
@@ -799,7 +853,21 @@ NS_GFN double ns_irls_step(double sig, const ns_work &w, int n, double maxmu, co
             n_lat += (unsigned)__reduce_add_sync(0xffffffffu, nlA);
         }
 #endif
-        for (int i = lane; i < n; i += G::nl()) {
+        int n_iter = n, i_first = lane, i_step = G::nl();
+#if defined(__CUDA_ARCH__)
+        ns_deflist dl(w.scratch, n);
+        if (per_thread) {
+            n_iter = dl.sort();
+            i_first = G::llane();
+            i_step = G::lnl();
+        }
+#endif
+        for (int it = i_first; it < n_iter; it += i_step) {
+            int i = it;
+#if defined(__CUDA_ARCH__)
+            if (per_thread)
+                i = dl.srt[it];
+#endif
             if (!(s_x[i] > 0))
                 continue;
             const double mu = s_mu[i], eta = s_eta[i], y = s_y[i];
@@ -808,9 +876,6 @@ NS_GFN double ns_irls_step(double sig, const ns_work &w, int n, double maxmu, co
             const double sV = sqrt(V);
 #if defined(__CUDA_ARCH__)
             if (MODE == 2) {
-                const double j1 = fmax(ceil(mu - c * sV), 0.0), j2 = floor(mu + c * sV);
-                if (per_thread && !(j2 - j1 + 1 > twon))
-                    continue; /* done above */
                 ns_E12_coop(mu, sig, c, prm.n_ai_sig_tukey, w.coop, res.cnt, &e1, &sap);
             } else
 #endif

@@ -1,5 +1,5 @@
 """Small fixed case for ncu: one ns_call_snv over a C2-shaped batch (100 samples) with enough
-common germline sites that k_fit_heavy has work.  Usage: python profiles/profile_case.py [P] [p_germline]"""
+common germline sites that k_fit_heavy has work.  Usage: python profiles/profile_case.py [P] [p_germline] [config]"""
 import os
 import sys
 import time
@@ -12,7 +12,8 @@ from needlestack_b200 import synth
 
 P = int(sys.argv[1]) if len(sys.argv) > 1 else 20000
 pg = float(sys.argv[2]) if len(sys.argv) > 2 else 1e-3
-ref, counts = synth.generate(synth.CONFIGS["C2"], P=P, seed=99, p_germline=pg)
+cfgname = sys.argv[3] if len(sys.argv) > 3 else "C2"
+ref, counts = synth.generate(synth.CONFIGS[cfgname], P=P, seed=99, p_germline=pg)
 with ns.Caller(0) as c:
     for rep in range(2):
         t = time.time()
