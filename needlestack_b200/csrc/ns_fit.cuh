@@ -537,7 +537,10 @@ NS_GFN double ns_sig_objective(double sig, const ns_work &w, int n, const ns_par
             int nsA = 0, nlA = 0;
             ns_deflist dl(w.scratch, n);
             dl.reset();
-            for (int i = G::lane() * 32 + lid; i < n; i += G::nl() * 32) {
+            /* consecutive samples go to consecutive CTAs of the cluster, so that every CTA gets its share of both
+             * the per-thread sums and the deferred list */
+            const int csz = G::nl() / G::lnl(), crk = G::lane() / G::lnl();
+            for (int i = (G::llane() * 32 + lid) * csz + crk; i < n; i += G::nl() * 32) {
                 if (!(w.x[i] > 0))
                     continue;
                 const double mu = w.mu[i], y = w.y[i];
@@ -811,7 +814,8 @@ NS_GFN double ns_irls_step(double sig, const ns_work &w, int n, double maxmu, co
             int nsA = 0, nlA = 0;
             ns_deflist dl(w.scratch, n);
             dl.reset();
-            for (int i = G::lane() * 32 + lid; i < n; i += G::nl() * 32) {
+            const int csz = G::nl() / G::lnl(), crk = G::lane() / G::lnl();
+            for (int i = (G::llane() * 32 + lid) * csz + crk; i < n; i += G::nl() * 32) {
                 if (!(s_x[i] > 0))
                     continue;
                 const double mu = s_mu[i], eta = s_eta[i], y = s_y[i];
