@@ -74,15 +74,16 @@ NS_GF inline double ns_ai_sum(double mui, double sig, double c, double j1, doubl
     double pm = ns_dnbinom_mu(j1, invsig, mui);
     double D = (j1 == 0) ? 0.0 : ns_digamma(j1 + invsig) - dg0; /* digamma(j+1/sig)-digamma(1/sig) */
     const double q = mui / (mui + invsig);
+    const double inv_csd = 1.0 / csd, inv_mpi = 1.0 / mpi; /* the loop itself is division-free */
     double acc = 0;
     for (double j = j1; j <= j2; j += 1) {
         double d = j - mui;
-        double t = d / csd;
+        double t = d * inv_csd;
         double w = (t * t - 1) * (t * t - 1);
-        double psi = D - lg - d / mpi;
+        double psi = D - lg - d * inv_mpi;
         acc += w * psi * pm;
         double ja = j + invsig, jb = j + 1;
-        double rr = 1.0 / (ja * jb);
+        double rr = ns_frcp(ja * jb); /* ja, jb >= 1e-1: normal and positive */
         pm *= (ja * ja) * rr * q; /* pmf(j+1)/pmf(j) = (j+size)/(j+1) * mu/(mu+size) */
         D += jb * rr;             /* digamma(x+1) = digamma(x) + 1/x */
     }
@@ -163,15 +164,16 @@ NS_GF inline void ns_E12_sum(double mui, double sig, double c, double j1, double
     const double size = 1 / sig, csd = c * sqrtV;
     double pm = ns_dnbinom_mu(j1, size, mui);
     const double q = mui / (mui + size);
+    const double inv_csd = 1.0 / csd;
     double a1 = 0, a2 = 0;
     for (double j = j1; j <= j2; j += 1) {
         double d = j - mui;
-        double t = d / csd;
+        double t = d * inv_csd;
         double w = (t * t - 1) * (t * t - 1);
         double wp = w * pm;
         a1 += wp * d;
         a2 += wp * (d * d);
-        pm *= ((j + size) / (j + 1)) * q;
+        pm *= ((j + size) * ns_frcp(j + 1)) * q;
     }
     e1 = a1 / sqrtV;
     e2 = a2 / sqrtV;
@@ -956,7 +958,14 @@ NS_GF inline void ns_fit_unit(const ns_work &w, int n, double maxmu, const ns_pa
     const double h25 = (double)(nfit - 1) * 0.25, h75 = (double)(nfit - 1) * 0.75;
     const int lo25 = (int)floor(h25), hi25 = (int)ceil(h25), lo75 = (int)floor(h75), hi75 = (int)ceil(h75);
     double v0 = 0, v1 = 0, v2 = 0, v3 = 0;
-    for (int i = lane; i < n; i += G::lnl()) {
+    int r_first = lane, r_step = G::lnl();
+#if defined(__CUDA_ARCH__)
+    if (MODE == 2) { /* the replicas of a warp would all count the same ranks: one sample per thread instead */
+        r_first = threadIdx.x;
+        r_step = blockDim.x;
+    }
+#endif
+    for (int i = r_first; i < n; i += r_step) {
         if (!(w.x[i] > 0))
             continue;
         double ai = w.eta[i];
@@ -974,6 +983,17 @@ NS_GF inline void ns_fit_unit(const ns_work &w, int n, double maxmu, const ns_pa
         if (rank == hi75)
             v3 = ai;
     }
+#if defined(__CUDA_ARCH__)
+    if (MODE == 2) { /* the collectives below take one value per warp */
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            v0 += __shfl_xor_sync(0xffffffffu, v0, o);
+            v1 += __shfl_xor_sync(0xffffffffu, v1, o);
+            v2 += __shfl_xor_sync(0xffffffffu, v2, o);
+            v3 += __shfl_xor_sync(0xffffffffu, v3, o);
+        }
+    }
+#endif
     v0 = G::lsum(v0);
     v1 = G::lsum(v1);
     v2 = G::lsum(v2);
