@@ -153,9 +153,61 @@ SEXP C_ns_call_snv(SEXP ctx, SEXP counts, SEXP ref, SEXP params, SEXP tn, SEXP e
     return res;
 }
 
+/* Explicit units (indel alleles of needlestack.r:461-567 / :624-730, the DP / AD units of annotate_vcf.r:57-69):
+ * dp, vp and the optional vm, rp, rm are integer matrices dim = c(n, U) (memory [U][n]); is_indel raw(U) or NULL.
+ * Returns per-unit sigma, slope, flags and the [n x U] GQ / q-value / p-value matrices of every unit (emit_mode ALL). */
+SEXP C_ns_call_units(SEXP ctx, SEXP dp, SEXP vp, SEXP vm, SEXP rp, SEXP rm, SEXP is_indel, SEXP params)
+{
+    ns_ctx *c = get_ctx(ctx);
+    ns_params p;
+    fill_params(params, &p, 1);
+    p.emit_mode = NS_EMIT_ALL;
+    SEXP dim = getAttrib(dp, R_DimSymbol);
+    const int n = INTEGER(dim)[0];
+    const int64_t U = INTEGER(dim)[1];
+    ns_out o;
+    memset(&o, 0, sizeof o);
+    const char *names[] = {"sigma", "slope", "flags", "pvalue", "qvalue", "gq", ""};
+    SEXP res = PROTECT(mkNamed(VECSXP, names));
+    SEXP v;
+    SET_VECTOR_ELT(res, 0, v = allocVector(REALSXP, U)); o.sigma = REAL(v);
+    SET_VECTOR_ELT(res, 1, v = allocVector(REALSXP, U)); o.slope = REAL(v);
+    SET_VECTOR_ELT(res, 2, v = allocVector(INTSXP, U));  o.flags = (uint32_t *)INTEGER(v);
+    SET_VECTOR_ELT(res, 3, v = allocMatrix(REALSXP, n, (int)U)); o.pvalue = REAL(v);
+    SET_VECTOR_ELT(res, 4, v = allocMatrix(REALSXP, n, (int)U)); o.qvalue = REAL(v);
+    SET_VECTOR_ELT(res, 5, v = allocMatrix(REALSXP, n, (int)U)); o.gq = REAL(v);
+    o.emit_cap = U;
+#define OPT(x) ((x) == R_NilValue ? NULL : INTEGER(x))
+    int rc = ns_call_units(c, &p, n, U, INTEGER(dp), INTEGER(vp), OPT(vm), OPT(rp), OPT(rm),
+                           is_indel == R_NilValue ? NULL : RAW(is_indel), 0, &o);
+#undef OPT
+    if (rc)
+        error("needlestack-b200: %s", ns_last_error(c));
+    UNPROTECT(1);
+    return res;
+}
+
+/* toQvalue(x, y) of plot_rob_nb.r:83-87 on a grid: gx, gy integer vectors of equal length */
+SEXP C_ns_qvalue_grid(SEXP ctx, SEXP sigma, SEXP slope, SEXP coverage, SEXP ma_count, SEXP gx, SEXP gy)
+{
+    ns_ctx *c = get_ctx(ctx);
+    const R_xlen_t m = XLENGTH(gx);
+    if (XLENGTH(gy) != m || XLENGTH(coverage) != XLENGTH(ma_count))
+        error("needlestack-b200: coverage/ma_count and gx/gy must have equal lengths");
+    SEXP q = PROTECT(allocVector(REALSXP, m));
+    int rc = ns_qvalue_grid(c, asReal(sigma), asReal(slope), (int)XLENGTH(coverage), INTEGER(coverage), INTEGER(ma_count),
+                            (int64_t)m, INTEGER(gx), INTEGER(gy), REAL(q));
+    if (rc)
+        error("needlestack-b200: %s", ns_last_error(c));
+    UNPROTECT(1);
+    return q;
+}
+
 static const R_CallMethodDef call_methods[] = {{"C_ns_create", (DL_FUNC)&C_ns_create, 1},
                                                {"C_ns_glmrob_nb", (DL_FUNC)&C_ns_glmrob_nb, 4},
                                                {"C_ns_call_snv", (DL_FUNC)&C_ns_call_snv, 6},
+                                               {"C_ns_call_units", (DL_FUNC)&C_ns_call_units, 8},
+                                               {"C_ns_qvalue_grid", (DL_FUNC)&C_ns_qvalue_grid, 7},
                                                {NULL, NULL, 0}};
 
 void R_init_ns_rshim(DllInfo *dll)
