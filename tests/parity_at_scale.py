@@ -17,7 +17,9 @@ import needlestack_b200 as ns  # noqa: E402
 from needlestack_b200 import synth  # noqa: E402
 
 CASES = [("C1", 40000, {}, False), ("C2", 16000, {}, False), ("C2", 4000, {"extra_rob": 1}, False),
-         ("C3", 48, {}, False), ("C4", 1500, {}, True), ("C5", 300000, {}, False)]
+         ("C3", 48, {}, False), ("C4", 1500, {}, True), ("C5", 300000, {}, False),
+         # the throughput regime of the cluster kernel (one CTA per unit, two-phase evaluation), forced on a small batch
+         ("C3", 48, {"_env": {"NS_HEAVY_CLUSTER": "1"}}, False)]
 
 
 def main(out_path):
@@ -25,6 +27,9 @@ def main(out_path):
     threads = os.cpu_count() or 1
     with ns.Caller(0) as c:
         for cfgname, P, kw, tn in CASES:
+            kw = dict(kw)
+            env = kw.pop("_env", {})
+            os.environ.update(env)
             cfg = synth.CONFIGS[cfgname]
             ref, counts = synth.generate(cfg, P=P, seed=cfg.seed + 7)
             pairs = synth.tn_pairs(cfg) if tn else None
@@ -46,7 +51,9 @@ def main(out_path):
             except AssertionError as e:
                 rep = dict(ok=False, error=str(e)[:2000])
             rep.pop("bad", None)
-            rep.update(config=cfgname, positions=P, params=kw, tn_pairs=tn, oracle_seconds=round(t_or, 2),
+            for k in env:
+                os.environ.pop(k, None)
+            rep.update(config=cfgname, positions=P, params=kw, env=env, tn_pairs=tn, oracle_seconds=round(t_or, 2),
                        oracle_threads=threads, gpu_seconds=round(t_gpu, 3), calls=int(O["gate2"].sum()),
                        heavy_units=int(c.timings()["n_heavy"]))
             rep = {k: (float(v) if isinstance(v, (np.floating,)) else v) for k, v in rep.items()}

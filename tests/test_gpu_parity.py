@@ -69,3 +69,18 @@ def test_skipped_reference_base_and_chunking(caller, oracle, monkeypatch):
     parity.compare(O, d, label="skipped")
     assert R.n_skipped == 3 * len(ref[::7])
     assert np.all(R.emit_index[np.repeat(ref > 3, 3)] == -1)
+
+
+def test_deep_panel_throughput_regime(caller, oracle, monkeypatch):
+    """One CTA per unit + the two-phase evaluation (lattice-sum windows one sample per thread, spline windows from the
+    sorted deferred list): the regime the launch picks for thousands of queued deep-panel units, forced here on a
+    small batch; also bitwise repeatable from run to run."""
+    for cl in ("1", "2"):
+        monkeypatch.setenv("NS_HEAVY_CLUSTER", cl)
+        rep, R = _run(caller, oracle, "C3", 16, 21, pv=0.1, pg=0.0)
+        assert R.n_quad > 0 and rep["n_fitted"] >= 40
+        cfg = synth.CONFIGS["C3"]
+        ref, counts = synth.generate(cfg, P=16, seed=21, p_variant=0.1, p_germline=0.0)
+        R2 = caller.call_snv(ref, counts, prm=make_params(emit_mode=NS_EMIT_ALL))
+        assert np.array_equal(R.sigma, R2.sigma, equal_nan=True) and np.array_equal(R.slope, R2.slope, equal_nan=True)
+        assert np.array_equal(R.dense("gq"), R2.dense("gq"), equal_nan=True)
