@@ -396,6 +396,25 @@ def main():
                "h2d_bytes_per_step": int(h_counts.nbytes + h_ref.nbytes), "d2h_bytes_per_step": int(d2h),
                "ms_per_step": ms_h / a.steps, "api": "needlestack_b200.Caller.call_snv -> ns_call_snv (C ABI)"}
         assert Rh.n_fitted == R.n_fitted and Rh.n_emitted == R.n_emitted
+        if int(d_counts.max().item()) < 65536:
+            # informational: the same call with the 16-bit wire format (ns_call_snv_u16); the headline e2e above is the
+            # reference-facing int32 form
+            h16 = ns.PinnedArray((P, 9, n), np.uint16)
+            torch.from_numpy(h16.array.view(np.int16)).copy_(d_counts.to(torch.int16))
+            torch.cuda.synchronize()
+            for _ in range(2):
+                R16 = caller.call_snv(h_ref.array, h16.array, prm=prm)
+            barrier()
+            e0.record()
+            for _ in range(a.steps):
+                R16 = caller.call_snv(h_ref.array, h16.array, prm=prm)
+            e1.record()
+            barrier()
+            ms16 = allmax(e0.elapsed_time(e1))
+            assert R16.n_fitted == R.n_fitted and R16.n_emitted == R.n_emitted
+            e2e["u16_wire_format"] = {"value": allsum(R16.n_fitted * a.steps) / (ms16 * 1e-3), "ms_per_step": ms16 / a.steps,
+                                      "h2d_bytes_per_step": int(h16.nbytes + h_ref.nbytes)}
+            h16.free()
         ref_np = h_ref.array[: min(P, 8192)].copy()
         counts_np = h_counts.array[: min(P, 8192)].copy()
     else:

@@ -157,6 +157,10 @@ int ns_get_timings(ns_ctx *ctx, ns_timings *t);
  */
 int ns_call_snv(ns_ctx *ctx, const ns_params *prm, int n_samples, int64_t n_positions,
                 const uint8_t *ref, const int32_t *counts, ns_out *out);
+/* same with 16-bit count planes (uint16 [P][9][n]; every count must fit): half the host-to-device bytes, widened
+ * to the int32 rows of the kernels on the device.  For WGS-like shapes, where the host link bounds the throughput. */
+int ns_call_snv_u16(ns_ctx *ctx, const ns_params *prm, int n_samples, int64_t n_positions,
+                    const uint8_t *ref, const uint16_t *counts, ns_out *out);
 /* same, inputs already resident on the context's device */
 int ns_call_snv_device(ns_ctx *ctx, const ns_params *prm, int n_samples, int64_t n_positions,
                        const uint8_t *d_ref, const int32_t *d_counts, ns_out *out);

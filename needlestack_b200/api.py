@@ -51,6 +51,7 @@ def load_library():
     L.ns_free_pinned.argtypes = [vp]
     L.ns_get_timings.argtypes = [vp, C.POINTER(NsTimings)]
     L.ns_call_snv.argtypes = [vp, C.POINTER(NsParams), C.c_int, C.c_int64, vp, vp, C.POINTER(NsOut)]
+    L.ns_call_snv_u16.argtypes = [vp, C.POINTER(NsParams), C.c_int, C.c_int64, vp, vp, C.POINTER(NsOut)]
     L.ns_call_snv_device.argtypes = [vp, C.POINTER(NsParams), C.c_int, C.c_int64, vp, vp, C.POINTER(NsOut)]
     L.ns_call_units.argtypes = [vp, C.POINTER(NsParams), C.c_int, C.c_int64, vp, vp, vp, vp, vp, vp, C.c_int,
                                 C.POINTER(NsOut)]
@@ -83,7 +84,7 @@ def load_library():
 
 EXPORTED_SYMBOLS = ("ns_abi_version", "ns_sizeof", "ns_params_glm_default", "ns_params_caller_default", "ns_create", "ns_destroy",
                     "ns_last_error", "ns_set_stream", "ns_alloc_pinned", "ns_free_pinned", "ns_get_timings",
-                    "ns_call_snv", "ns_call_snv_device", "ns_call_units", "ns_glmrob_nb", "ns_qvalue_grid", "ns_measure_fp64_peak",
+                    "ns_call_snv", "ns_call_snv_u16", "ns_call_snv_device", "ns_call_units", "ns_glmrob_nb", "ns_qvalue_grid", "ns_measure_fp64_peak",
                     "ns_table_parse", "ns_table_free", "ns_table_positions", "ns_table_samples",
                     "ns_table_counts_pinned", "ns_table_counts", "ns_table_ref", "ns_table_ref_text", "ns_table_loc",
                     "ns_table_chrom", "ns_table_n_chrom", "ns_table_chrom_name", "ns_table_indel_cov",
@@ -312,15 +313,18 @@ class Caller:
 
     # -- the reference's per-allele SNV loop (needlestack.r:321-413) -----------------------
     def call_snv(self, ref, counts, prm=None, emit_cap=None, want_rows=True, **kw):
-        """ref uint8 [P] (0..3 = A,T,C,G), counts int32 [P][9][n] (depth,A,T,C,G,a,t,c,g), host arrays."""
+        """ref uint8 [P] (0..3 = A,T,C,G), counts int32 [P][9][n] (depth,A,T,C,G,a,t,c,g), host arrays.  A uint16
+        `counts` array takes the narrow wire format (ns_call_snv_u16: half the host-to-device bytes)."""
         prm = prm or make_params(**kw)
-        counts = np.ascontiguousarray(counts, dtype=np.int32)
+        u16 = getattr(counts, "dtype", None) == np.uint16
+        counts = np.ascontiguousarray(counts, dtype=np.uint16 if u16 else np.int32)
         ref = np.ascontiguousarray(ref, dtype=np.uint8)
         P, nine, n = counts.shape
         if nine != 9 or len(ref) != P:
             raise ValueError("counts must be [P][9][n] and ref [P]")
-        return self._run(lambda o: self._L.ns_call_snv(self._ctx, C.byref(prm), n, P, _ptr(ref), _ptr(counts),
-                                                       C.byref(o)), prm, 3 * P, n, emit_cap, want_rows)
+        fn = self._L.ns_call_snv_u16 if u16 else self._L.ns_call_snv
+        return self._run(lambda o: fn(self._ctx, C.byref(prm), n, P, _ptr(ref), _ptr(counts), C.byref(o)),
+                         prm, 3 * P, n, emit_cap, want_rows)
 
     def call_snv_device(self, d_ref_ptr, d_counts_ptr, P, n, prm, emit_cap=None, want_rows=True):
         """same with device-resident inputs (raw device pointers, e.g. torch tensor .data_ptr())"""

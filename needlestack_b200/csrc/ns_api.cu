@@ -86,6 +86,7 @@ struct ns_ctx {
     DevBuf<uint8_t> in_ref[2];
     DevBuf<int32_t> in_rows[5];
     DevBuf<uint8_t> in_indel;
+    DevBuf<uint16_t> in_counts16[2];
     DevBuf<double> grid_out;
     cudaEvent_t ev_h2d[2], ev_free[2];
     /* per-chunk unit arrays */
@@ -238,6 +239,8 @@ void ns_destroy(ns_ctx *ctx)
     for (int i = 0; i < 5; i++)
         ctx->in_rows[i].release();
     ctx->in_indel.release();
+    ctx->in_counts16[0].release();
+    ctx->in_counts16[1].release();
     ctx->grid_out.release();
     ctx->flags.release(), ctx->iters.release(), ctx->cycles.release(), ctx->sigma.release(), ctx->slope.release(), ctx->max_gq.release();
     ctx->needrow.release(), ctx->row.release(), ctx->emitflag.release(), ctx->emitidx.release();
@@ -794,12 +797,28 @@ int ns_call_snv_device(ns_ctx *ctx, const ns_params *prm, int n, int64_t P, cons
     return NS_OK;
 }
 
-int ns_call_snv(ns_ctx *ctx, const ns_params *prm, int n, int64_t P, const uint8_t *ref, const int32_t *counts,
-                ns_out *out)
+/* 16-bit planes widened on the device: WGS-like shapes are bound by the host link (1.8 KB per position at n = 50),
+ * and exome / genome depths fit 16 bits, so the narrow wire format halves the transfer; the kernels keep int32 rows */
+__global__ void k_widen16(const uint16_t *__restrict__ src, int32_t *__restrict__ dst, size_t n)
+{
+    const size_t n8 = n / 8;
+    const uint4 *s8 = reinterpret_cast<const uint4 *>(src);
+    int4 *d4 = reinterpret_cast<int4 *>(dst);
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (size_t)gridDim.x * blockDim.x) {
+        const uint4 v = __ldg(s8 + i);
+        d4[2 * i] = make_int4((int)(v.x & 0xffffu), (int)(v.x >> 16), (int)(v.y & 0xffffu), (int)(v.y >> 16));
+        d4[2 * i + 1] = make_int4((int)(v.z & 0xffffu), (int)(v.z >> 16), (int)(v.w & 0xffffu), (int)(v.w >> 16));
+    }
+    for (size_t i = 8 * n8 + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        dst[i] = (int32_t)src[i];
+}
+
+static int ns_call_snv_host(ns_ctx *ctx, const ns_params *prm, int n, int64_t P, const uint8_t *ref, const int32_t *counts,
+                            const uint16_t *counts16, ns_out *out)
 {
     if (!ctx)
         return NS_ERR_ARG;
-    if (!prm || !out || n < 1 || P < 0 || (P > 0 && (!ref || !counts))) {
+    if (!prm || !out || n < 1 || P < 0 || (P > 0 && (!ref || (!counts && !counts16)))) {
         ctx->err = "ns_call_snv: bad argument";
         return NS_ERR_ARG;
     }
@@ -825,9 +844,21 @@ int ns_call_snv(ns_ctx *ctx, const ns_params *prm, int n, int64_t P, const uint8
             ctx->err = std::string("device allocation (input staging) failed: ") + cudaGetErrorString(e);
             return NS_ERR_NOMEM;
         }
+        if (counts16 && (e = ctx->in_counts16[buf].reserve((size_t)pc * row_elems))) {
+            ctx->err = std::string("device allocation (input staging) failed: ") + cudaGetErrorString(e);
+            return NS_ERR_NOMEM;
+        }
         CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_free[buf], 0));
-        CK(cudaMemcpyAsync(ctx->in_counts[buf].p, counts + (size_t)p0 * row_elems, (size_t)pc * row_elems * sizeof(int32_t),
-                           cudaMemcpyHostToDevice, ctx->copy_stream));
+        if (counts16) {
+            const size_t ne = (size_t)pc * row_elems;
+            CK(cudaMemcpyAsync(ctx->in_counts16[buf].p, counts16 + (size_t)p0 * row_elems, ne * sizeof(uint16_t),
+                               cudaMemcpyHostToDevice, ctx->copy_stream));
+            k_widen16<<<ctx->sm_count * 4, 256, 0, ctx->copy_stream>>>(ctx->in_counts16[buf].p, ctx->in_counts[buf].p, ne);
+            CK(cudaGetLastError());
+            ctx->tm.kernel_launches++;
+        } else
+            CK(cudaMemcpyAsync(ctx->in_counts[buf].p, counts + (size_t)p0 * row_elems, (size_t)pc * row_elems * sizeof(int32_t),
+                               cudaMemcpyHostToDevice, ctx->copy_stream));
         CK(cudaMemcpyAsync(ctx->in_ref[buf].p, ref + p0, (size_t)pc, cudaMemcpyHostToDevice, ctx->copy_stream));
         CK(cudaEventRecord(ctx->ev_h2d[buf], ctx->copy_stream));
         return NS_OK;
@@ -870,6 +901,18 @@ int ns_call_snv(ns_ctx *ctx, const ns_params *prm, int n, int64_t P, const uint8
         return NS_ERR_EMIT_OVERFLOW;
     }
     return NS_OK;
+}
+
+int ns_call_snv(ns_ctx *ctx, const ns_params *prm, int n, int64_t P, const uint8_t *ref, const int32_t *counts,
+                ns_out *out)
+{
+    return ns_call_snv_host(ctx, prm, n, P, ref, counts, nullptr, out);
+}
+
+int ns_call_snv_u16(ns_ctx *ctx, const ns_params *prm, int n, int64_t P, const uint8_t *ref, const uint16_t *counts,
+                    ns_out *out)
+{
+    return ns_call_snv_host(ctx, prm, n, P, ref, nullptr, counts, out);
 }
 
 int ns_call_units(ns_ctx *ctx, const ns_params *prm, int n, int64_t U, const int32_t *dp, const int32_t *vp,

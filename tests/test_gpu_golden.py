@@ -162,3 +162,19 @@ def test_tn_index_validation(caller):
     G = golden_util.load("c1_default")
     with pytest.raises(ns.NeedlestackError, match="out of range"):
         caller.call_snv(G["ref"], G["counts"], prm=make_params(pairs=dict(tindex=[0], nindex=[99])))
+
+
+def test_u16_wire_format_is_identical(caller):
+    """ns_call_snv_u16: the 16-bit planes are widened on the device; results are those of the int32 call, bit for bit"""
+    import numpy as np
+    from needlestack_b200 import NS_EMIT_ALL, make_params, synth
+    ref, counts = synth.generate(synth.CONFIGS["C2"], P=1501, seed=77, p_variant=0.02, p_germline=0.002)
+    assert counts.max() < 65536
+    prm = make_params(emit_mode=NS_EMIT_ALL)
+    A = caller.call_snv(ref, counts, prm=prm)
+    B = caller.call_snv(ref, counts.astype(np.uint16), prm=prm)
+    assert A.n_fitted == B.n_fitted > 50 and A.n_emitted == B.n_emitted
+    for k in ("sigma", "slope", "flags", "max_gq"):
+        assert np.array_equal(A[k], B[k], equal_nan=True), k
+    for k in ("pvalue", "gq", "qval_minaf", "sor", "gt", "status"):
+        assert np.array_equal(A.dense(k), B.dense(k), equal_nan=True), k
