@@ -21,6 +21,9 @@
 
 #define NS_JTAB 64  /* digamma-difference table entries per sigma */
 #define NS_RTAB 256 /* reciprocals 1/j, j = 1..255 */
+#ifndef NS_PT_FACTOR
+#define NS_PT_FACTOR 2 /* two-phase evaluation of the cluster kernel from this many samples per warp */
+#endif
 #define NS_STEP_BY 16.0 /* knot spacing up to which the spline knots are reached by lattice recurrence */
 
 /* The hot functions are out of line, so the compiler no longer sees that the working set lives in
@@ -528,7 +531,7 @@ NS_GFN double ns_sig_objective(double sig, const ns_work &w, int n, const ns_par
 #if defined(__CUDA_ARCH__)
         /* throughput regime only: with few samples per warp (a unit on a full cluster) the lanes sharing one
          * window is the shorter critical path */
-        const bool per_thread = (MODE == 2) && n >= 4 * G::nl();
+        const bool per_thread = (MODE == 2) && n >= NS_PT_FACTOR * G::nl();
         if (per_thread) {
             /* Windows that stay on the lattice-sum branch (<= 2 n_ai points; 94 % of the sample evaluations of a
              * deep panel, 25 points on average) are taken one sample per THREAD, serially: with the warp's lanes
@@ -808,7 +811,7 @@ NS_GFN double ns_irls_step(double sig, const ns_work &w, int n, double maxmu, co
         }
     } else {
 #if defined(__CUDA_ARCH__)
-        const bool per_thread = (MODE == 2) && n >= 4 * G::nl();
+        const bool per_thread = (MODE == 2) && n >= NS_PT_FACTOR * G::nl();
         if (per_thread) {
             /* lattice-sum windows: one sample per thread (see ns_sig_objective) */
             const int lid = threadIdx.x & 31;
