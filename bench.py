@@ -256,9 +256,9 @@ def main():
     dev = torch.device("cuda", local_rank)
     dist = None
     if world > 1:
-        # keep stdout to the one JSON line (NCCL prints its version banner there at VERSION level)
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"
+        # keep stdout to the one JSON line: at any NCCL_DEBUG level NCCL prints its version banner there
+        if not os.environ.get("NS_KEEP_NCCL_DEBUG"):
+            os.environ.pop("NCCL_DEBUG", None)
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
 
