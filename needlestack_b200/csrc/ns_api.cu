@@ -443,8 +443,7 @@ static cudaError_t ns_launch_heavy(ns_ctx *ctx, cudaStream_t st, int n, int n_un
         return e;
     if (cl > 8 && (e = cudaFuncSetAttribute(k_fit_heavy, cudaFuncAttributeNonPortableClusterSizeAllowed, 1)))
         return e;
-    cudaLaunchConfig_t cfg;
-    memset(&cfg, 0, sizeof(cfg));
+    cudaLaunchConfig_t cfg = {};
     cfg.blockDim = dim3(threads);
     cfg.dynamicSmemBytes = smh;
     cfg.stream = st;
