@@ -77,7 +77,7 @@ __device__ __forceinline__ void ns_cspline_pivots(ns_cpiv &P, int n, double j1, 
         if (i > iw) {
             /* the first half of the warm-up only has to be right to ~1e-7: its error is
              * damped by more than 1e-10 before the lane's own rows */
-            double t = (i < i0 - 10) ? dm * (double)__frcp_rn((float)bp) : dm / bp;
+            double t = (i < i0 - 10) ? dm * (double)__frcp_rn((float)bp) : dm * ns_frcp(bp); /* pivots are >= 2 */
             bi = bi - t * dm;
         }
         bp = bi;
@@ -97,7 +97,7 @@ __device__ __forceinline__ void ns_cspline_pivots(ns_cpiv &P, int n, double j1, 
             double bi = 2 * (dm + di);
             double t = 0;
             if (i > 1) { /* i == iw can only happen for i == 1 here (iw < i0 unless i0 == 1) */
-                t = dm / bp;
+                t = dm * ns_frcp(bp);
                 bi = bi - t * dm;
             }
             P.piv[k] = bi;
@@ -157,7 +157,7 @@ __device__ __forceinline__ void ns_cspline_solve(const ns_cpiv &P, const ns_coop
         Bk[k] = 0.0;
         Ak[k] = 1.0;
         if (i0 + k <= nu) {
-            double ib = 1.0 / P.piv[k];
+            double ib = ns_frcp(P.piv[k]);
             Bk[k] = rp[k] * ib;
             Ak[k] = -P.aup[k] * ib;
             B = Bk[k] + Ak[k] * B;
@@ -311,10 +311,10 @@ struct ns_k21_coop {
         resasc = rasc * dhlgth;
         abserr = fabs((resk - resg) * hlgth);
         if (resasc != 0.0 && abserr != 0.0) {
-            double r = abserr * 200.0 / resasc;
-            abserr = resasc * fmin(1.0, r * sqrt(r));
+            double r = abserr * 200.0 * ns_frcp(resasc); /* both positive and normal here */
+            abserr = resasc * fmin(1.0, r * ns_fsqrt(r));
         }
-        if (resabs > uflow / (epmach * 50.0))
+        if (resabs > NS_DBL_MIN / (NS_DBL_EPS * 50.0))
             abserr = fmax(epmach * 50.0 * resabs, abserr);
     }
 };
@@ -381,7 +381,7 @@ static __device__ __noinline__ double ns_ai_coop(double mui, double sig, double 
                 acc += w * (D - lg - d * inv_mpi) * pm;
                 double ja = j + invsig;
                 pm *= (ja * ns_rcp_int(sc.rt, sc.rtn, j + 1)) * q;
-                D += 1.0 / ja;
+                D += ns_frcp(ja);
             }
         }
         return ns_wsum(acc);
