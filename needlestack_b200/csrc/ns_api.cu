@@ -411,9 +411,13 @@ static void ns_heavy_geometry(int n, int n_units, int sm_count, int *threads, in
     if (eth && (atoi(eth) == 128 || atoi(eth) == 256 || atoi(eth) == 512))
         th = atoi(eth);
     const int wpc = th / 32;
-    int c = 1;
-    while (c < 8 && c * wpc < n)
-        c <<= 1; /* enough warps for one sample per warp, up to the portable cluster size 8 */
+    /* just enough CTAs for one sample per warp, up to the portable cluster size 8 (n = 100: 7 CTAs of 16 warps -
+     * a power of two would hold an eighth SM whose warps have no sample; C2 step 371 -> 361 ms) */
+    int c = (n + wpc - 1) / wpc;
+    if (c > 8)
+        c = 8;
+    if (c < 1)
+        c = 1;
     /* many queued units (deep panels: every unit takes this kernel): throughput matters more than the
      * latency of one unit, and smaller clusters waste fewer warps at the barriers */
     while (c > 1 && n_units > 8 * (sm_count / c))
