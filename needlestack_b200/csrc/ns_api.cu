@@ -408,8 +408,8 @@ static void ns_heavy_geometry(int n, int n_units, int sm_count, int *threads, in
 {
     int th = NS_HEAVY_THREADS;
     const char *eth = getenv("NS_HEAVY_THREADS");
-    if (eth && (atoi(eth) == 128 || atoi(eth) == 256 || atoi(eth) == 512))
-        th = atoi(eth);
+    if (eth && (atoi(eth) == 128 || atoi(eth) == 256 || atoi(eth) == 512 || atoi(eth) == NS_HEAVY_THREADS_TP))
+        th = atoi(eth); /* tests and experiments; NS_HEAVY_THREADS_TP selects the throughput form of the kernel */
     const int wpc = th / 32;
     /* just enough CTAs for one sample per warp, up to the portable cluster size 8 (n = 100: 7 CTAs of 16 warps -
      * a power of two would hold an eighth SM whose warps have no sample; C2 step 371 -> 361 ms) */
@@ -420,8 +420,12 @@ static void ns_heavy_geometry(int n, int n_units, int sm_count, int *threads, in
         c = 1;
     /* many queued units (deep panels: every unit takes this kernel): throughput matters more than the
      * latency of one unit, and smaller clusters waste fewer warps at the barriers */
+    const int c_latency = c;
     while (c > 1 && n_units > 8 * (sm_count / c))
         c >>= 1;
+    /* down to one CTA per unit it is the throughput form of the kernel (k_fit_heavy_tp: 20 warps, 96 registers) */
+    if (c == 1 && c_latency > 1 && !eth)
+        th = NS_HEAVY_THREADS_TP;
     const char *ecl = getenv("NS_HEAVY_CLUSTER");
     if (ecl && atoi(ecl) >= 1 && atoi(ecl) <= 16)
         c = atoi(ecl);
@@ -442,10 +446,11 @@ static cudaError_t ns_launch_heavy(ns_ctx *ctx, cudaStream_t st, int n, int n_un
     int threads, cl;
     ns_heavy_geometry(n, n_units_max, ctx->sm_count, &threads, &cl);
     const size_t smh = ns_heavy_smem(n, threads);
+    auto kern = threads == NS_HEAVY_THREADS_TP ? k_fit_heavy_tp : k_fit_heavy;
     cudaError_t e;
-    if (smh > 48 * 1024 && (e = cudaFuncSetAttribute(k_fit_heavy, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smh)))
+    if (smh > 48 * 1024 && (e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smh)))
         return e;
-    if (cl > 8 && (e = cudaFuncSetAttribute(k_fit_heavy, cudaFuncAttributeNonPortableClusterSizeAllowed, 1)))
+    if (cl > 8 && (e = cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1)))
         return e;
     cudaLaunchConfig_t cfg = {};
     cfg.blockDim = dim3(threads);
@@ -460,7 +465,7 @@ static cudaError_t ns_launch_heavy(ns_ctx *ctx, cudaStream_t st, int n, int n_un
     cfg.numAttrs = 1;
     cfg.gridDim = dim3(cl);
     int ncl = 0;
-    e = cudaOccupancyMaxActiveClusters(&ncl, k_fit_heavy, &cfg);
+    e = cudaOccupancyMaxActiveClusters(&ncl, kern, &cfg);
     if (e != cudaSuccess)
         return e;
     if (ncl < 1)
@@ -472,7 +477,7 @@ static cudaError_t ns_launch_heavy(ns_ctx *ctx, cudaStream_t st, int n, int n_un
     int *started = which == 0 ? ctx->d_started : nullptr;
     if (n_clusters_out)
         *n_clusters_out = ncl;
-    return cudaLaunchKernelEx(&cfg, k_fit_heavy, src, dprm, u0, ua, cp, which, started);
+    return cudaLaunchKernelEx(&cfg, kern, src, dprm, u0, ua, cp, which, started);
 }
 
 static float ev_ms(cudaEvent_t a, cudaEvent_t b)

@@ -132,8 +132,8 @@ k_fit(ns_unit_src src, const __grid_constant__ ns_params prm, int64_t u0, ns_uni
 #ifndef NS_HEAVY_MINB
 #define NS_HEAVY_MINB 1 /* 128 registers; 64 (to leave half the register file to the warp kernel) spills and is 1.8x slower */
 #endif
-__global__ void __launch_bounds__(NS_HEAVY_THREADS, NS_HEAVY_MINB)
-k_fit_heavy(ns_unit_src src, const __grid_constant__ ns_params prm, int64_t u0, ns_unit_arrays ua, ns_counters *cnt, int which, int *started)
+static __device__ __forceinline__ void ns_fit_heavy_body(const ns_unit_src &src, const ns_params &prm, int64_t u0,
+                                                         const ns_unit_arrays &ua, ns_counters *cnt, int which, int *started)
 {
     const int n = src.n;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -202,4 +202,18 @@ k_fit_heavy(ns_unit_src src, const __grid_constant__ ns_params prm, int64_t u0, 
         atomicAdd(&cnt->n_lattice, tot_lat);
         atomicAdd(&cnt->n_quad, tot_quad);
     }
+}
+
+/* latency form: 16 warps per CTA at 128 registers (a unit's critical path is what a small batch waits for) */
+__global__ void __launch_bounds__(NS_HEAVY_THREADS, NS_HEAVY_MINB)
+k_fit_heavy(ns_unit_src src, const __grid_constant__ ns_params prm, int64_t u0, ns_unit_arrays ua, ns_counters *cnt, int which, int *started)
+{
+    ns_fit_heavy_body(src, prm, u0, ua, cnt, which, started);
+}
+
+/* throughput form, for deep panels with thousands of queued units: 20 warps per CTA at 96 registers (C3 +10 %) */
+__global__ void __launch_bounds__(NS_HEAVY_THREADS_TP, 1)
+k_fit_heavy_tp(ns_unit_src src, const __grid_constant__ ns_params prm, int64_t u0, ns_unit_arrays ua, ns_counters *cnt, int which, int *started)
+{
+    ns_fit_heavy_body(src, prm, u0, ua, cnt, which, started);
 }

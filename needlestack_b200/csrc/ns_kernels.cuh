@@ -11,6 +11,7 @@
 
 #define NS_COOP_DOUBLES (4 * NS_MAX_KNOTS)
 #define NS_RTAB_HEAVY 4096
+#define NS_HEAVY_THREADS_TP 640 /* throughput form of the cluster kernel: 20 warps per CTA, 96 registers */
 #ifndef NS_HEAVY_THREADS
 #define NS_HEAVY_THREADS 512 /* 16 warps per CTA x 8 CTAs per cluster = one sample per warp at n <= 128 */
 #endif
@@ -45,6 +46,8 @@ __global__ void k_gate(ns_unit_src src, ns_params prm, int64_t u0, int n_units, 
 __global__ void k_fit(ns_unit_src src, const __grid_constant__ ns_params prm, int64_t u0, ns_unit_arrays ua, ns_counters *cnt);
 __global__ void k_fit_heavy(ns_unit_src src, const __grid_constant__ ns_params prm, int64_t u0, ns_unit_arrays ua, ns_counters *cnt,
                             int which, int *started);
+__global__ void k_fit_heavy_tp(ns_unit_src src, const __grid_constant__ ns_params prm, int64_t u0, ns_unit_arrays ua, ns_counters *cnt,
+                               int which, int *started);
 __global__ void k_post(ns_unit_src src, ns_params prm, int64_t u0, ns_unit_arrays ua, ns_planes pl,
                        const double *qtab, int qtab_len, ns_counters *cnt);
 __global__ void k_scan_total(const int *flag, const int *excl, int n, int *total);

@@ -9,7 +9,7 @@ import sys
 
 TAG = sys.argv[1] if len(sys.argv) > 1 else "r1"
 SRC, DST = "gpurun_out", "profiles"
-OURS = ("k_gate", "k_fit_heavy", "k_fit", "k_post", "k_pack", "k_qtab", "k_dfma", "k_scan_total", "k_qgrid", "DeviceScan")
+OURS = ("k_gate", "k_fit_heavy_tp", "k_fit_heavy", "k_fit", "k_post", "k_pack", "k_qtab", "k_dfma", "k_scan_total", "k_qgrid", "DeviceScan")
 
 
 def short(name):

@@ -19,7 +19,7 @@ from needlestack_b200 import synth  # noqa: E402
 CASES = [("C1", 40000, {}, False), ("C2", 16000, {}, False), ("C2", 4000, {"extra_rob": 1}, False),
          ("C3", 48, {}, False), ("C4", 1500, {}, True), ("C5", 300000, {}, False),
          # the throughput regime of the cluster kernel (one CTA per unit, two-phase evaluation), forced on a small batch
-         ("C3", 48, {"_env": {"NS_HEAVY_CLUSTER": "1"}}, False)]
+         ("C3", 48, {"_env": {"NS_HEAVY_CLUSTER": "1", "NS_HEAVY_THREADS": "640"}}, False)]
 
 
 def main(out_path):

@@ -75,8 +75,10 @@ def test_deep_panel_throughput_regime(caller, oracle, monkeypatch):
     """One CTA per unit + the two-phase evaluation (lattice-sum windows one sample per thread, spline windows from the
     sorted deferred list): the regime the launch picks for thousands of queued deep-panel units, forced here on a
     small batch; also bitwise repeatable from run to run."""
-    for cl in ("1", "2"):
+    for cl, th in (("1", None), ("2", None), ("1", "640")):  # 640 threads = the throughput form k_fit_heavy_tp
         monkeypatch.setenv("NS_HEAVY_CLUSTER", cl)
+        if th:
+            monkeypatch.setenv("NS_HEAVY_THREADS", th)
         rep, R = _run(caller, oracle, "C3", 16, 21, pv=0.1, pg=0.0)
         assert R.n_quad > 0 and rep["n_fitted"] >= 40
         cfg = synth.CONFIGS["C3"]
