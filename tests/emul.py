@@ -30,7 +30,7 @@ def lib():
     if _LIB is None:
         L = C.CDLL(build())
         d = C.c_double
-        for name, nargs in (("emul_dnbinom_mu", 3), ("emul_nb_pvalue", 3), ("emul_digamma", 1), ("emul_fexp", 1), ("emul_flog", 1), ("emul_flog_tab", 1), ("emul_fexp_bf", 1),
+        for name, nargs in (("emul_dnbinom_mu", 3), ("emul_nb_pvalue", 3), ("emul_nb_pvalue_lb", 3), ("emul_digamma", 1), ("emul_fexp", 1), ("emul_flog", 1), ("emul_flog_tab", 1), ("emul_fexp_bf", 1),
                             ("emul_qnbinom_mu", 3), ("emul_qbinom", 3), ("emul_fisher", 4)):
             f = getattr(L, name)
             f.restype = d

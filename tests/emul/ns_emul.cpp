@@ -90,6 +90,7 @@ double emul_nb_pvalue(double y, double size, double mu) { return ns_nb_pvalue(y,
 double emul_digamma(double x) { return ns_digamma(x); }
 double emul_fexp(double x) { return ns_fexp(x); }
 double emul_flog(double x) { return ns_flog(x); }
+double emul_nb_pvalue_lb(double y, double size, double mu) { return ns_nb_pvalue_lb(y, size, mu); }
 double emul_flog_tab(double x) { return ns_flog_tab(x, ns_h_logtab); }
 double emul_fexp_bf(double x) { return ns_fexp_bf(x); }
 double emul_qnbinom_mu(double p, double size, double mu) { return ns_qnbinom_mu(p, size, mu); }

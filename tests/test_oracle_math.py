@@ -283,3 +283,29 @@ def test_zeroin_brent(L):
     assert L.orc_uniroot(g, None, 1e-3, 10.0, 1e-8, 50, C.byref(root), C.byref(ne)) != 0
     h = CB(lambda x, _: float("nan"))
     assert L.orc_uniroot(h, None, 1e-3, 10.0, 1e-8, 50, C.byref(root), C.byref(ne)) != 0
+
+
+def test_pvalue_lower_bound_and_fast_math_helpers():
+    """ns_nb_pvalue_lb (the post kernel's call test) never exceeds the exact tail probability and equals it where the
+    direct sum applies; ns_flog_tab / ns_fexp_bf (the window seed of k_fit) stay within 1 ulp of mpmath."""
+    import mpmath as mp
+    import emul
+    L = emul.lib()
+    rng = np.random.default_rng(12)
+    n_eq = 0
+    for _ in range(4000):
+        size = 1.0 / 10 ** rng.uniform(-3, 1)
+        mu = 10 ** rng.uniform(-3, 2.5)
+        y = float(rng.integers(0, 60))
+        exact, lb = L.emul_nb_pvalue(y, size, mu), L.emul_nb_pvalue_lb(y, size, mu)
+        assert lb <= exact * (1 + 1e-12) + 1e-300, (y, size, mu, lb, exact)
+        n_eq += lb == exact
+    assert n_eq > 1000
+    mp.mp.dps = 40
+    for x in np.concatenate([1 + 10 ** rng.uniform(-15, 0, 300), 10 ** rng.uniform(0, 7, 300)]):
+        got, want = L.emul_flog_tab(float(x)), mp.log(mp.mpf(float(x)))
+        assert abs((mp.mpf(got) - want) / want) < 2 ** -52 * 1.01
+    for x in -10 ** rng.uniform(-12, 2.84, 600):
+        got, want = L.emul_fexp_bf(float(x)), mp.exp(mp.mpf(float(x)))
+        assert abs((mp.mpf(got) - want) / want) < 2 ** -52
+    assert L.emul_fexp_bf(-5000.0) == 0.0
