@@ -397,19 +397,23 @@ static __device__ __noinline__ double ns_ai_coop(double mui, double sig, double 
              * difference directly at each knot */
             double j = ns_cknot(j1, j2, by, n_ai, k0);
             double pm = ns_dnbinom_mu(j, invsig, mui);
+            /* digamma(j + 1/sig) - digamma(1/sig): one evaluation at the lane's first knot, then the recurrence
+             * digamma(x + 1) = digamma(x) + 1/x along the walk (a digamma per knot cost more than the <= 16 steps) */
+            double D = (j == 0) ? 0.0 : ns_digamma(j + invsig) - dg0;
             int k = k0;
             double xk = j;
             for (;; j += 1) {
                 if (j == xk) {
                     double t = (j - mui) * inv_csd;
                     double w = (t * t - 1) * (t * t - 1);
-                    double D = (j == 0) ? 0.0 : ns_digamma(j + invsig) - dg0;
                     sc.y[k] = w * (D - lg - (j - mui) * inv_mpi) * pm;
                     if (++k == k1)
                         break;
                     xk = ns_cknot(j1, j2, by, n_ai, k);
                 }
-                pm *= ((j + invsig) * ns_rcp_int(sc.rt, sc.rtn, j + 1)) * q;
+                const double ja = j + invsig;
+                pm *= (ja * ns_rcp_int(sc.rt, sc.rtn, j + 1)) * q;
+                D += ns_frcp(ja);
             }
         } else {
             for (int k = k0; k < k1; k++) {
