@@ -108,3 +108,24 @@ def test_huge_depths_take_the_64_bit_inversion_test(caller, oracle):
     assert np.array_equal((R.flags & NS_F_GATED) != 0, O["gated"] != 0) and R.n_fitted == 0
     inv = ((R.flags & NS_F_REF_INV) != 0).reshape(P, 3)
     assert inv[1, 0] and not inv[0, 0] and inv[3, 0]  # unit 0 of a REF = A position is the T allele
+
+
+def test_unaligned_device_planes_take_the_scalar_path(caller):
+    """ns_call_snv_device with count planes that are only 4-byte aligned: the vector-load forms do not apply; the
+    result is that of the aligned call, bit for bit"""
+    import torch
+    cfg = dataclasses.replace(synth.CONFIGS["C1"], n=100)
+    ref, counts = synth.generate(cfg, P=400, seed=31, p_variant=0.03, p_germline=0.01)
+    prm = make_params(emit_mode=NS_EMIT_ALL)
+    A = caller.call_snv(ref, counts, prm=prm)
+    buf = torch.zeros(counts.size + 4, dtype=torch.int32, device="cuda")
+    d_ref = torch.from_numpy(ref).cuda()
+    for off in (1, 2):  # 4- and 8-byte aligned
+        view = buf[off:off + counts.size]
+        view.copy_(torch.from_numpy(counts.reshape(-1)))
+        torch.cuda.synchronize()
+        assert view.data_ptr() % 16 != 0
+        B = caller.call_snv_device(d_ref.data_ptr(), view.data_ptr(), 400, 100, prm)
+        assert np.array_equal(A.flags, B.flags)
+        assert np.array_equal(A.sigma, B.sigma, equal_nan=True) and np.array_equal(A.slope, B.slope, equal_nan=True)
+        assert np.array_equal(A.dense("gq"), B.dense("gq"), equal_nan=True)
