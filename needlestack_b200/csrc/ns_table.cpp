@@ -19,6 +19,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <vector>
@@ -37,6 +38,7 @@ struct ns_table {
     int64_t P = 0;
     int32_t *counts = nullptr;
     bool counts_pinned = false;
+    size_t counts_cap = 0; /* bytes of the page-locked buffer (it may come from the pool and be larger) */
     std::vector<uint8_t> ref;
     std::vector<int64_t> loc;
     std::vector<int32_t> chrom;
@@ -52,6 +54,51 @@ struct ns_table {
 };
 
 namespace {
+
+/* One cached page-locked buffer: the driver parses chunk after chunk of the same size, and cudaMallocHost /
+ * cudaFreeHost of a gigabyte each cost more than parsing it (the loader ran at 1.3 GB/s end to end against 1.9 GB/s
+ * for the parse alone).  A released buffer is kept for the next table that fits; a larger request replaces it. */
+std::mutex g_pool_mu;
+void *g_pool_ptr = nullptr;
+size_t g_pool_cap = 0;
+
+void *pinned_acquire(size_t bytes, size_t &cap)
+{
+    {
+        std::lock_guard<std::mutex> lk(g_pool_mu);
+        if (g_pool_ptr && g_pool_cap >= bytes && g_pool_cap <= 2 * bytes + (64u << 20)) {
+            void *p = g_pool_ptr;
+            cap = g_pool_cap;
+            g_pool_ptr = nullptr;
+            g_pool_cap = 0;
+            return p;
+        }
+    }
+    void *p = nullptr;
+    if (cudaMallocHost(&p, bytes) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    cap = bytes;
+    return p;
+}
+
+void pinned_release(void *p, size_t cap)
+{
+    void *drop = nullptr;
+    {
+        std::lock_guard<std::mutex> lk(g_pool_mu);
+        if (!g_pool_ptr || g_pool_cap < cap) {
+            drop = g_pool_ptr;
+            g_pool_ptr = p;
+            g_pool_cap = cap;
+        } else {
+            drop = p;
+        }
+    }
+    if (drop)
+        cudaFreeHost(drop);
+}
 
 struct Chunk {
     const char *beg, *end;
@@ -286,7 +333,7 @@ ns_table *ns_table_parse(const char *text, size_t len, int n_samples, int has_he
     if (bytes) {
         int ndev = 0;
         if (cudaGetDeviceCount(&ndev) == cudaSuccess && ndev > 0 &&
-            cudaMallocHost((void **)&t->counts, bytes) == cudaSuccess) {
+            (t->counts = (int32_t *)pinned_acquire(bytes, t->counts_cap)) != nullptr) {
             t->counts_pinned = true;
         } else {
             cudaGetLastError();
@@ -314,7 +361,7 @@ ns_table *ns_table_parse(const char *text, size_t len, int n_samples, int has_he
         if (!ck.err.empty()) {
             std::string m = ck.err;
             if (t->counts_pinned)
-                cudaFreeHost(t->counts);
+                pinned_release(t->counts, t->counts_cap);
             else
                 free(t->counts);
             delete t;
@@ -356,7 +403,7 @@ void ns_table_free(ns_table *t)
         return;
     if (t->counts) {
         if (t->counts_pinned)
-            cudaFreeHost(t->counts);
+            pinned_release(t->counts, t->counts_cap);
         else
             free(t->counts);
     }
