@@ -40,6 +40,13 @@ def rfmt(x, digits=7, nan="NA"):
         return "Inf" if x > 0 else "-Inf"
     if x == 0:
         return "0"
+    if digits == 7 and 1e-4 <= abs(x) < 1e7:
+        # C's %g makes the same choice of digits in this range and stays in fixed notation (checked against the
+        # general path on 4e5 random values in tests/test_loader_driver.py); 6 x faster, and a VCF record formats
+        # ~600 numbers
+        t = "%.7g" % x
+        if "e" not in t:
+            return t
     mant, exp = f"{x:.{digits - 1}e}".split("e")
     kp = int(exp)
     nsig = len(mant.replace("-", "").replace(".", "").rstrip("0")) or 1
@@ -220,15 +227,18 @@ def vcf_line(chrom, pos, ref_txt, alt_txt, typ, row, dp, vp, vm, rp, rm, sigma, 
     fmt = "GT:" + ("QVAL_INV" if inv else "QVAL") + ":DP:RO:AO:AF:SB:SOR:RVSB:FS:QVAL_minAF:STATUS"
     st = _status_text(row["status"], names)
     cols = [chrom, str(pos), ".", ref_txt, alt_txt, rfmt(max_gq), ".", info, fmt]
-    for i in range(len(dp)):
-        cols.append(":".join([GT_TEXT[int(row["gt"][i])], rfmt(gq[i]), str(int(dp[i])), str(int(rp[i] + rm[i])),
-                              str(int(ma[i])), rfmt(af_s[i], nan="NaN"), f"{int(rp[i])},{int(rm[i])},{int(vp[i])},{int(vm[i])}",
-                              rfmt(row["sor"][i]), rfmt(row["rvsb"][i]), rfmt(row["fs"][i]), rfmt(row["qval_minaf"][i]),
-                              st[i]]))
+    # plain Python numbers from here on: numpy scalars cost more to index and convert than to format
+    gtl, gql, afl = np.asarray(row["gt"]).tolist(), np.asarray(gq, dtype=float).tolist(), np.asarray(af_s, dtype=float).tolist()
+    dpl, rpl, rml, vpl, vml = (np.asarray(a).tolist() for a in (dp, rp, rm, vp, vm))
+    sorl, rvl, fsl, qml = (np.asarray(row[k], dtype=float).tolist() for k in ("sor", "rvsb", "fs", "qval_minaf"))
+    for i in range(len(dpl)):
+        cols.append(":".join([GT_TEXT[gtl[i]], rfmt(gql[i]), str(dpl[i]), str(rpl[i] + rml[i]),
+                              str(vpl[i] + vml[i]), rfmt(afl[i], nan="NaN"), f"{rpl[i]},{rml[i]},{vpl[i]},{vml[i]}",
+                              rfmt(sorl[i]), rfmt(rvl[i]), rfmt(fsl[i]), rfmt(qml[i]), st[i]]))
     return "\t".join(cols) + "\n"
 
 
-def call_table(caller, T, o, names, pairs=None, fasta=None):
+def call_table(caller, T, o, names, pairs=None, fasta=None, caller_indel=None):
     """all VCF records of one parsed table chunk, in the reference's order: per line the SNV alleles,
     then the deletions, then the insertions"""
     n = T.n
@@ -239,6 +249,23 @@ def call_table(caller, T, o, names, pairs=None, fasta=None):
                           SB_threshold_SNV=o["SB_threshold_SNV"], SB_threshold_indel=o["SB_threshold_indel"],
                           sigma_normal=o["sigma"], afmin_power=o["afmin_power"],
                           output_all_SNVs=int(o["output_all_SNVs"]), emit_mode=api.NS_EMIT_CALLS)
+    # the indel alleles of the chunk go through a second context (its own stream) while the SNV planes are on the
+    # first: a chunk holds few indel units, and one cluster-path unit among them otherwise adds its whole critical path
+    indel_job = None
+    if len(T.indel_pos):
+        dp, vp, vm, rp, rm, ind = T.indel_unit_rows()
+        if caller_indel is not None:
+            import threading
+            box = {}
+
+            def run_indels():
+                try:
+                    box["I"] = caller_indel.call_units(dp, vp, vm, rp, rm, is_indel=ind, prm=prm)
+                except BaseException as e:
+                    box["err"] = e
+
+            indel_job = threading.Thread(target=run_indels)
+            indel_job.start()
     S = caller.call_snv(T.ref, T.counts, prm=prm)
     recs = []  # (position row, order key, text)
     keys = ("gq", "qval_minaf", "sor", "rvsb", "fs", "gt", "status", "pooled")
@@ -256,8 +283,13 @@ def call_table(caller, T, o, names, pairs=None, fasta=None):
                        before, after)
         recs.append((p, k, txt))
     if len(T.indel_pos):
-        dp, vp, vm, rp, rm, ind = T.indel_unit_rows()
-        I = caller.call_units(dp, vp, vm, rp, rm, is_indel=ind, prm=prm)
+        if indel_job is not None:
+            indel_job.join()
+            if "err" in box:
+                raise box["err"]
+            I = box["I"]
+        else:
+            I = caller.call_units(dp, vp, vm, rp, rm, is_indel=ind, prm=prm)
         for e, u in enumerate(I.emit_unit):
             u = int(u)
             p = int(T.indel_pos[u])
@@ -299,21 +331,41 @@ def main(argv=None, stdin=None):
     if os.path.exists(o["out_file"]):
         os.remove(o["out_file"])
     n = len(names)
-    with open(o["out_file"], "a") as out, api.Caller(o["device"]) as caller:
-        out.write(vcf_header(o, names, pairs is not None))
-        while True:
-            lines = []
-            for _ in range(o["chunk"]):
-                ln = src.readline()
-                if not ln:
+    # a reader thread parses chunk k+1 (C++, outside the GIL) while chunk k is on the GPU; two tables in flight
+    import queue
+    import threading
+    q = queue.Queue(maxsize=1)
+
+    def reader():
+        try:
+            while True:
+                lines = []
+                for _ in range(o["chunk"]):
+                    ln = src.readline()
+                    if not ln:
+                        break
+                    lines.append(ln)
+                if not lines:
                     break
-                lines.append(ln)
-            if not lines:
+                q.put(readcounts.load_table(b"".join(lines), n, has_header=False))
+            q.put(None)
+        except BaseException as e:  # surfaced in the main thread
+            q.put(e)
+
+    th = threading.Thread(target=reader, daemon=True)
+    with open(o["out_file"], "a") as out, api.Caller(o["device"]) as caller, api.Caller(o["device"]) as caller2:
+        out.write(vcf_header(o, names, pairs is not None))
+        th.start()
+        while True:
+            T = q.get()
+            if T is None:
                 break
-            T = readcounts.load_table(b"".join(lines), n, has_header=False)
-            for txt in call_table(caller, T, o, names, pairs, fasta):
+            if isinstance(T, BaseException):
+                raise T
+            for txt in call_table(caller, T, o, names, pairs, fasta, caller_indel=caller2):
                 out.write(txt)
             T.close()
+    th.join()
     return 0
 
 

@@ -88,3 +88,23 @@ def test_cli_defaults_and_header(tmp_path):
     (tmp_path / "pairs.txt").write_text("TUMOR NORMAL\nS S_1\nT NA\n")
     pr = driver.read_pairs(str(tmp_path / "pairs.txt"), names)
     assert pr == dict(tindex=[0], nindex=[1], only_t=[2], only_n=[])
+
+
+def test_r_number_formatting_fast_path_equals_general_path():
+    """rfmt's %g shortcut (1e-4 <= |x| < 1e7) against the general construction on random values and the edges"""
+    import random
+    from needlestack_b200 import driver
+
+    def general(x):
+        mant, exp = f"{x:.6e}".split("e")
+        nsig = len(mant.replace("-", "").replace(".", "").rstrip("0")) or 1
+        return f"{x:.{max(0, nsig - 1 - int(exp))}f}"
+
+    random.seed(3)
+    vals = [10 ** random.uniform(-4, 7) * random.choice([1, -1]) for _ in range(200000)]
+    vals += [round(v, random.randint(0, 6)) for v in vals[:50000]]
+    vals += [0.0001, 9999999.4, 9999999.5, 9999999.999, 0.00010000004, 99999.995, 0.30000000000000004, 1234567.0, 5e-5,
+             123.4567891, 1e6, 0.1]
+    for x in vals:
+        if x != 0:
+            assert driver.rfmt(x) == general(x), x
