@@ -24,7 +24,7 @@
 #ifndef NS_PT_FACTOR
 #define NS_PT_FACTOR 2 /* two-phase evaluation of the cluster kernel from this many samples per warp */
 #endif
-#define NS_STEP_BY 16.0 /* knot spacing up to which the spline knots are reached by lattice recurrence */
+#define NS_STEP_BY 32.0 /* knot spacing up to which the spline knots are reached by lattice recurrence (a direct pmf + digamma per knot costs ~25 recurrence steps) */
 
 /* The hot functions are out of line, so the compiler no longer sees that the working set lives in
  * shared memory and would emit generic loads (LD + address translation).  In the fast path the
