@@ -31,6 +31,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 METRIC = "site-alleles fitted/sec (robust NB + p/q-values)"
 UNIT = "site-alleles/s"
+REF_SAMPLE_POSITIONS = 8192  # positions of the batch the CPU arm samples (numpy generator, same bytes in both arms)
 
 
 def parse():
@@ -186,18 +187,49 @@ def cpu_oracle_rate(ref_np, counts_np, n_threads, target_s, prm_kw):
         t = time.perf_counter()
         O = orc.call_snv_batch(ref_np[:Ps], c, prm, n_threads=n_threads)
         dt = time.perf_counter() - t
-        return dt, int((O["gated"] == 0).sum())
+        return dt, int((O["gated"] == 0).sum()), O
 
     Pmax = len(ref_np)
     Ps = min(Pmax, 64 * n_threads)
-    dt, nf = run(Ps)
+    dt, nf, O = run(Ps)
     if dt < target_s / 3 and Ps < Pmax:
         Ps2 = int(min(Pmax, max(Ps, Ps * target_s / max(dt, 1e-3))))
         Ps2 -= Ps2 % n_threads
         if Ps2 > Ps:
             Ps = Ps2
-            dt, nf = run(Ps)
-    return dict(value=nf / dt, fitted=nf, seconds=dt, positions=Ps)
+            dt, nf, O = run(Ps)
+    return dict(value=nf / dt, fitted=nf, seconds=dt, positions=Ps, oracle=O)
+
+
+def parity_check(caller, ns, ref_np, counts_np, O, Ps):
+    """The CUDA path (through the C ABI, host buffers) against the oracle's outputs on the first Ps positions of
+    the BENCHMARKED batch, outside every timed region: ties the headline number to a correctness statement."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import parity
+    R = caller.call_snv(ref_np[:Ps], counts_np[:Ps], prm=ns.make_params(emit_mode=ns.NS_EMIT_ALL))
+    d = {k: R.dense(k) for k in ("pvalue", "qvalue", "gq", "qval_minaf", "sor", "rvsb", "fs", "pooled")}
+    d["gt"] = R.dense("gt", fill=0)
+    d["status"] = R.dense("status", fill=0)
+    for k in ("sigma", "slope", "max_gq", "flags", "n_outer", "n_irls", "n_obj"):
+        d[k] = np.array(R[k])
+    try:
+        rep = parity.compare(O, d, label="bench batch")
+        bad = 0
+    except AssertionError as e:
+        rep = {"error": str(e)[:600]}
+        bad = -1
+    keep = ("n_units", "n_fitted", "calls", "calls_compared", "nonconverged", "nonconverged_compared", "gate_mismatch",
+            "gt_mismatch", "status_mismatch", "maxit_mismatch", "iter_mismatch", "irls_mismatch", "obj_mismatch",
+            "near_threshold", "sigma_abs_rule_only", "sigma_within_tol_only", "max_rel_sigma", "max_abs_sigma",
+            "max_rel_slope", "max_d_gq", "max_rel_p", "error")
+    out = {k: rep[k] for k in keep if k in rep}
+    out["units"] = out.pop("n_units", 3 * Ps)
+    out["fitted"] = out.pop("n_fitted", None)
+    out["mismatches"] = bad if bad else int(rep["gate_mismatch"] + rep["gt_mismatch"] + rep["status_mismatch"] +
+                                             rep["maxit_mismatch"])
+    out["positions"] = int(Ps)
+    out["tolerance"] = "flags/GT/STATUS bit-exact; sigma, slope rel 1e-6 (sigma abs 2e-8 / 1e-6 counted); p, q, Phred 1e-6"
+    return out
 
 
 def main():
@@ -222,8 +254,8 @@ def main():
         # here), all host cores, bounded sample of the same workload per step
         if rank != 0:
             return 0
-        Ps = min(P, 4096)
-        ref_np, counts_np = synth.generate(cfg, P=Ps, seed=cfg.seed)
+        Ps = min(P, REF_SAMPLE_POSITIONS)
+        ref_np, counts_np = synth.generate(cfg, P=Ps, seed=cfg.seed, p_germline=a.p_germline)
         rates = []
         t_all = time.perf_counter()
         per = max(2.0, min(20.0, 120.0 / max(1, a.steps + a.warmup)))
@@ -241,7 +273,7 @@ def main():
                 "data": "synthetic", "config": config,
                 "cpu_baseline": {"value": val, "unit": UNIT, "cores": ncores, "kind": "port",
                                  "sample": f"{res['positions']} positions ({res['fitted']} fitted site-alleles) "
-                                           f"per step, C oracle (restatement of glm_rob_nb.r/needlestack.r; R "
+                                           f"per step = the first positions of the b200 arm's rank-0 batch, C oracle (restatement of glm_rob_nb.r/needlestack.r; R "
                                            f"absent), {ncores} pthreads"},
                 "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0}
@@ -283,6 +315,13 @@ def main():
         return float(t.item())
 
     d_ref, d_counts = generate_torch(cfg, P, cfg.seed + 1000 * rank, dev, a.p_germline)
+    # the first positions of every rank's batch come from the numpy generator: for rank 0 they are exactly the sample the
+    # reference arm (--impl reference) and the cpu_baseline / parity_check legs run the CPU oracle on
+    Ph = min(P, REF_SAMPLE_POSITIONS)
+    h_ref0, h_counts0 = synth.generate(cfg, P=Ph, seed=cfg.seed + 1000 * rank, p_germline=a.p_germline)
+    d_ref[:Ph] = torch.from_numpy(h_ref0).to(dev)
+    d_counts[:Ph] = torch.from_numpy(h_counts0).to(dev)
+    del h_ref0, h_counts0
     torch.cuda.synchronize()
     caller = ns.Caller(local_rank, reuse_outputs=True)  # results land in the Caller's pinned buffers
     caller.set_stream(torch.cuda.current_stream().cuda_stream)
@@ -396,8 +435,8 @@ def main():
                "h2d_bytes_per_step": int(h_counts.nbytes + h_ref.nbytes), "d2h_bytes_per_step": int(d2h),
                "ms_per_step": ms_h / a.steps, "api": "needlestack_b200.Caller.call_snv -> ns_call_snv (C ABI)"}
         assert Rh.n_fitted == R.n_fitted and Rh.n_emitted == R.n_emitted
-        ref_np = h_ref.array[: min(P, 8192)].copy()
-        counts_np = h_counts.array[: min(P, 8192)].copy()
+        ref_np = h_ref.array[: min(P, REF_SAMPLE_POSITIONS)].copy()
+        counts_np = h_counts.array[: min(P, REF_SAMPLE_POSITIONS)].copy()
         h_counts.free()  # at most one set of page-locked planes per rank at a time
         if int(d_counts.max().item()) < 65536:
             # informational: the same call with the 16-bit wire format (ns_call_snv_u16); the headline e2e above is the
@@ -419,22 +458,24 @@ def main():
                                       "h2d_bytes_per_step": int(h16.nbytes + h_ref.nbytes)}
             h16.free()
     else:
-        ref_np = d_ref[: min(P, 8192)].cpu().numpy()
-        counts_np = d_counts[: min(P, 8192)].cpu().numpy()
+        ref_np = d_ref[: min(P, REF_SAMPLE_POSITIONS)].cpu().numpy()
+        counts_np = d_counts[: min(P, REF_SAMPLE_POSITIONS)].cpu().numpy()
 
     cpu = None
+    parity_rep = None
     if rank == 0 and world == 1 and not a.no_cpu:
         r = cpu_oracle_rate(ref_np, counts_np, ncores, a.cpu_seconds, {})
         cpu = {"value": r["value"], "unit": UNIT, "cores": ncores, "kind": "port",
                "sample": f"first {r['positions']} positions of the same batch ({r['fitted']} fitted site-alleles, "
                          f"{r['seconds']:.1f} s), C oracle (restatement of glm_rob_nb.r/needlestack.r; R is not "
                          f"installed on this image), {ncores} pthreads"}
+        parity_rep = parity_check(caller, ns, ref_np, counts_np, r["oracle"], r["positions"])
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps,
                 "warmup": a.warmup, "ms_per_step": ms_max / a.steps, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config, "clocks": clocks,
                 "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "roofline_gate": roofline_gate,
-                "cpu_baseline": cpu,
+                "cpu_baseline": cpu, "parity_check": parity_rep,
                 "detail": {"site_alleles_processed_per_s": units_all / (ms_max * 1e-3),
                            "gate_pass_fraction": fitted_all / units_all, "fitted_per_step_rank0": R.n_fitted,
                            "emitted_per_step_rank0": n_emitted,

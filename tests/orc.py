@@ -183,22 +183,20 @@ def call_snv_batch(ref, counts, prm, n_threads=1):
                              _bp(gt), _bp(st), info)
     out["gt"] = gt
     out["status"] = st
-    ia = np.frombuffer(info, dtype=np.dtype(UnitInfo)) if False else None
-    out["sigma"] = np.array([info[u].glm.sigma for u in range(U)])
-    out["slope"] = np.array([info[u].glm.slope for u in range(U)])
-    out["gated"] = np.array([info[u].glm.gated for u in range(U)], dtype=np.int32)
-    out["extra_rob"] = np.array([info[u].glm.extra_rob for u in range(U)], dtype=np.int32)
-    out["ref_inv"] = np.array([info[u].ref_inv for u in range(U)], dtype=np.int32)
-    out["gate1"] = np.array([info[u].gate1 for u in range(U)], dtype=np.int32)
-    out["gate2"] = np.array([info[u].gate2 for u in range(U)], dtype=np.int32)
-    out["max_gq"] = np.array([info[u].max_gq for u in range(U)])
-    out["n_outer"] = np.array([info[u].glm.n_outer for u in range(U)], dtype=np.int32)
-    out["maxit_hit"] = np.array([info[u].glm.maxit_hit for u in range(U)], dtype=np.int32)
-    out["quad_error"] = np.array([info[u].glm.quad_error for u in range(U)], dtype=np.int32)
-    out["n_seed"] = np.array([info[u].glm.n_seed for u in range(U)], dtype=np.int64)
-    out["n_lattice"] = np.array([info[u].glm.n_lattice for u in range(U)], dtype=np.int64)
-    out["n_quad"] = np.array([info[u].glm.n_quad for u in range(U)], dtype=np.int64)
-    out["pooled"] = np.array([list(info[u].pooled) for u in range(U)])
+    ia = np.frombuffer(info, dtype=np.dtype(UnitInfo))  # structured view: no per-unit Python loop
+    g = ia["glm"]
+    out["sigma"] = g["sigma"].copy()
+    out["slope"] = g["slope"].copy()
+    for k, src in (("gated", "gated"), ("extra_rob", "extra_rob"), ("n_outer", "n_outer"), ("n_irls", "n_irls"),
+                   ("n_obj", "n_obj_eval"), ("maxit_hit", "maxit_hit"), ("quad_error", "quad_error"),
+                   ("sig_at_min", "sig_at_min"), ("nan_rows", "nan_rows")):
+        out[k] = g[src].astype(np.int32)
+    for k in ("ref_inv", "gate1", "gate2"):
+        out[k] = ia[k].astype(np.int32)
+    out["max_gq"] = ia["max_gq"].copy()
+    for k in ("n_seed", "n_lattice", "n_quad"):
+        out[k] = g[k].astype(np.int64)
+    out["pooled"] = ia["pooled"].reshape(U, 8).copy()
     out["info"] = info
     return out
 
