@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define NS_ABI_VERSION 1
+#define NS_ABI_VERSION 2
 
 /* ---- error codes ---------------------------------------------------------------- */
 #define NS_OK 0
@@ -128,6 +128,10 @@ typedef struct ns_timings {
     int64_t n_heavy; /* units that took the spline + quadrature kernel */
     int64_t n_deferred; /* ... of which the warp kernel handed over (not predicted by the gate kernel) */
     uint64_t fast_seed, fast_lattice; /* work counters of the warp kernel alone (k_fit) */
+    /* call-wide pool of cluster-path units (ABI 2) */
+    int64_t pool_units;  /* units whose fit ran in the pool, joined once at the end of the call */
+    int64_t chunks;      /* chunks this context processed */
+    double pool_tail_ms; /* time the end of the call waited for the pool's last units */
 } ns_timings;
 
 typedef struct ns_ctx ns_ctx;

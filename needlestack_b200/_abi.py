@@ -1,7 +1,7 @@
 """ctypes mirror of include/ns_b200.h (struct layouts and constants only)."""
 import ctypes as C
 
-NS_ABI_VERSION = 1
+NS_ABI_VERSION = 2
 
 NS_OK = 0
 NS_ERR_CUDA = -1
@@ -65,7 +65,8 @@ class NsOut(C.Structure):
 class NsTimings(C.Structure):
     _fields_ = [(k, C.c_double) for k in ("h2d_ms", "gate_ms", "fit_ms", "heavy_ms", "post_ms", "pack_ms", "d2h_ms",
                                           "total_ms", "heavy_pre_ms", "fit_phase_ms")] + [("kernel_launches", C.c_int64), ("n_heavy", C.c_int64), ("n_deferred", C.c_int64),
-                                                            ("fast_seed", C.c_uint64), ("fast_lattice", C.c_uint64)]
+                                                            ("fast_seed", C.c_uint64), ("fast_lattice", C.c_uint64),
+                                                            ("pool_units", C.c_int64), ("chunks", C.c_int64), ("pool_tail_ms", C.c_double)]
 
 
 GLM_DEFAULTS = dict(  # bin/glm_rob_nb.r:16-18

@@ -10,6 +10,8 @@
  *   k_post   p/q/GQ, Holm power q-values, T/N status, strand bias, genotypes
  *            (glm_rob_nb.r:219-224, needlestack.r:340-409)
  *   k_pack   gathers the rows of the emitted units, in unit order, for the D2H copy
+ * Units that take the cluster-per-unit kernel (spline + quadrature windows) leave the chunk: they go to a
+ * call-wide pool (HeavyPool) that runs on side streams next to later chunks and is joined once per call.
  * There is no CPU implementation behind this file: without a CUDA device ns_create() fails.
  */
 #include <cuda_runtime.h>
@@ -17,100 +19,15 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <string>
 #include <vector>
 
 #include "ns_kernels.cuh"
-
-/* ---- host side ----------------------------------------------------------------------- */
-template <class T> struct DevBuf {
-    T *p = nullptr;
-    size_t cap = 0;
-    cudaError_t reserve(size_t n)
-    {
-        if (n <= cap)
-            return cudaSuccess;
-        if (p)
-            cudaFree(p);
-        p = nullptr;
-        cap = 0;
-        size_t want = n + n / 8 + 64;
-        cudaError_t e = cudaMalloc((void **)&p, want * sizeof(T));
-        if (e == cudaSuccess)
-            cap = want;
-        return e;
-    }
-    void release()
-    {
-        if (p)
-            cudaFree(p);
-        p = nullptr;
-        cap = 0;
-    }
-};
-
-struct PlaneSet {
-    DevBuf<double> pvalue, qvalue, gq, qval_minaf, sor, rvsb, fs, pooled;
-    DevBuf<uint8_t> gt, status;
-    cudaError_t reserve(size_t rows, int n)
-    {
-        cudaError_t e;
-        size_t m = rows * (size_t)n;
-        if ((e = pvalue.reserve(m)) || (e = qvalue.reserve(m)) || (e = gq.reserve(m)) || (e = qval_minaf.reserve(m)) ||
-            (e = sor.reserve(m)) || (e = rvsb.reserve(m)) || (e = fs.reserve(m)) || (e = pooled.reserve(rows * 8)) ||
-            (e = gt.reserve(m)) || (e = status.reserve(m)))
-            return e;
-        return cudaSuccess;
-    }
-    ns_planes view()
-    {
-        ns_planes v = {pvalue.p, qvalue.p, gq.p, qval_minaf.p, sor.p, rvsb.p, fs.p, pooled.p, gt.p, status.p};
-        return v;
-    }
-    void release()
-    {
-        pvalue.release(), qvalue.release(), gq.release(), qval_minaf.release(), sor.release(), rvsb.release(),
-            fs.release(), pooled.release(), gt.release(), status.release();
-    }
-};
-
-struct ns_ctx {
-    int device = 0;
-    int sm_count = 148;
-    cudaStream_t stream = nullptr, own_stream = nullptr, copy_stream = nullptr, heavy_stream = nullptr;
-    cudaEvent_t ev_fork, ev_join, ev_h0, ev_h1;
-    std::string err;
-    /* staging of host inputs, double buffered */
-    DevBuf<int32_t> in_counts[2];
-    DevBuf<uint8_t> in_ref[2];
-    DevBuf<int32_t> in_rows[5];
-    DevBuf<uint8_t> in_indel;
-    DevBuf<uint16_t> in_counts16[2];
-    DevBuf<double> grid_out;
-    cudaEvent_t ev_h2d[2], ev_free[2];
-    /* per-chunk unit arrays */
-    DevBuf<uint32_t> flags, iters;
-    DevBuf<unsigned long long> cycles;
-    DevBuf<double> sigma, slope, max_gq;
-    DevBuf<int> needrow, row, emitflag, emitidx, fit_list, post_list, heavy_list, pre_list, emit_index_out;
-    DevBuf<int64_t> emit_unit;
-    DevBuf<ns_counters> counters;
-    DevBuf<unsigned char> cub_tmp;
-    PlaneSet rows, packed;
-    size_t packed_cap = 0;
-    /* parameter-dependent device state */
-    DevBuf<int32_t> pair_idx;
-    DevBuf<uint8_t> role;
-    DevBuf<double> qtabN, qtabT;
-    double qtab_sigma = -1, qtab_afmin = -2;
-    /* timings */
-    cudaEvent_t ev[10];
-    ns_timings tm;
-    ns_counters *h_counters = nullptr; /* pinned */
-    int *h_started = nullptr, *d_started = nullptr; /* mapped pinned flag written by k_fit_heavy */
-    int64_t chunk_units = 0;           /* 0 = auto */
-};
+#include "ns_hostmerge.hpp"
+#include "ns_api_internal.hpp"
 
 #define CK(call)                                                                                   \
     do {                                                                                           \
@@ -122,6 +39,107 @@ struct ns_ctx {
             return NS_ERR_CUDA;                                                                    \
         }                                                                                          \
     } while (0)
+
+
+/* ---- page-locked growable host planes ----------------------------------------------------------- */
+void HostRows::release()
+{
+    double **dpl[] = {&p.pvalue, &p.qvalue, &p.gq, &p.qval_minaf, &p.sor, &p.rvsb, &p.fs, &p.pooled};
+    for (double **d : dpl) {
+        if (*d)
+            cudaFreeHost(*d);
+        *d = nullptr;
+    }
+    if (p.gt)
+        cudaFreeHost(p.gt);
+    if (p.status)
+        cudaFreeHost(p.status);
+    if (p.emit_unit)
+        cudaFreeHost(p.emit_unit);
+    p.gt = p.status = nullptr;
+    p.emit_unit = nullptr;
+    cap = 0;
+}
+
+bool HostRows::reserve(int64_t rows, int n_samples, int64_t keep)
+{
+    if (rows <= cap && n_samples == n)
+        return true;
+    if (n_samples != n)
+        keep = 0;
+    int64_t want = rows + rows / 2 + 256;
+    ns_row_planes q = {};
+    const size_t rb = (size_t)n_samples * sizeof(double);
+    bool ok = true;
+    auto al = [&](void **dst, size_t bytes) {
+        if (ok && cudaHostAlloc(dst, bytes ? bytes : 1, cudaHostAllocPortable) != cudaSuccess) {
+            *dst = nullptr;
+            ok = false;
+        }
+    };
+    al((void **)&q.pvalue, want * rb), al((void **)&q.qvalue, want * rb), al((void **)&q.gq, want * rb);
+    al((void **)&q.qval_minaf, want * rb), al((void **)&q.sor, want * rb), al((void **)&q.rvsb, want * rb);
+    al((void **)&q.fs, want * rb), al((void **)&q.gt, want * (size_t)n_samples), al((void **)&q.status, want * (size_t)n_samples);
+    al((void **)&q.pooled, want * 8 * sizeof(double)), al((void **)&q.emit_unit, want * sizeof(int64_t));
+    if (!ok) {
+        HostRows tmp;
+        tmp.p = q;
+        tmp.release();
+        return false;
+    }
+    if (keep > 0 && cap > 0)
+        ns_rows_copy(q, 0, p, 0, keep, n_samples);
+    release();
+    p = q;
+    cap = want;
+    n = n_samples;
+    return true;
+}
+
+RowSink ns_sink_from_out(ns_out *out)
+{
+    RowSink s;
+    s.p.pvalue = out->pvalue, s.p.qvalue = out->qvalue, s.p.gq = out->gq, s.p.qval_minaf = out->qval_minaf;
+    s.p.sor = out->sor, s.p.rvsb = out->rvsb, s.p.fs = out->fs, s.p.gt = out->gt, s.p.status = out->status;
+    s.p.pooled = out->pooled, s.p.emit_unit = out->emit_unit;
+    s.cap = out->emit_cap;
+    s.want_rows = out->pvalue || out->qvalue || out->gq || out->qval_minaf || out->sor || out->rvsb || out->fs ||
+                  out->gt || out->status || out->pooled || out->emit_unit;
+    return s;
+}
+
+/* grant a kernel its dynamic shared memory once per size (the attribute call was re-issued for every chunk) */
+template <class K> static cudaError_t ns_need_smem(ns_ctx *ctx, int slot, K kern, size_t bytes)
+{
+    if (bytes <= 48 * 1024 || bytes <= ctx->smem_set[slot])
+        return cudaSuccess;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e == cudaSuccess)
+        ctx->smem_set[slot] = bytes;
+    return e;
+}
+
+/* wait for everything this context has in flight: called on every error return, so that no copy is still reading
+ * the caller's host buffers (or writing the caller's outputs) when the call hands control back */
+void ns_drain(ns_ctx *ctx)
+{
+    if (!ctx)
+        return;
+    cudaSetDevice(ctx->device);
+    if (ctx->copy_stream)
+        cudaStreamSynchronize(ctx->copy_stream);
+    if (ctx->heavy_stream)
+        cudaStreamSynchronize(ctx->heavy_stream);
+    for (int i = 0; i < NS_POOL_STREAMS; i++)
+        if (ctx->pool.streams[i])
+            cudaStreamSynchronize(ctx->pool.streams[i]);
+    if (ctx->stream)
+        cudaStreamSynchronize(ctx->stream);
+    ctx->pool.n_used = ctx->pool.n_launch = 0;
+    for (int i = 0; i < NS_POOL_STREAMS; i++)
+        ctx->pool.used[i] = false;
+    cudaGetLastError();
+}
 
 extern "C" {
 
@@ -195,6 +213,7 @@ ns_ctx *ns_create(int device, char *err, size_t errlen)
     ns_ctx *ctx = new ns_ctx();
     ctx->device = device;
     ctx->sm_count = prop.multiProcessorCount;
+    memset(&ctx->tm, 0, sizeof(ctx->tm));
     bool ok = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) == cudaSuccess &&
               cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) == cudaSuccess &&
               cudaStreamCreateWithFlags(&ctx->heavy_stream, cudaStreamNonBlocking) == cudaSuccess &&
@@ -206,6 +225,15 @@ ns_ctx *ns_create(int device, char *err, size_t errlen)
              cudaEventCreateWithFlags(&ctx->ev_free[i], cudaEventDisableTiming) == cudaSuccess;
     for (int i = 0; i < 10 && ok; i++)
         ok = cudaEventCreate(&ctx->ev[i]) == cudaSuccess;
+    HeavyPool &pl = ctx->pool;
+    for (int i = 0; i < NS_POOL_STREAMS && ok; i++)
+        ok = cudaStreamCreateWithFlags(&pl.streams[i], cudaStreamNonBlocking) == cudaSuccess &&
+             cudaEventCreateWithFlags(&pl.ev_done[i], cudaEventDisableTiming) == cudaSuccess &&
+             cudaEventCreate(&pl.ev_t0[i]) == cudaSuccess && cudaEventCreate(&pl.ev_t1[i]) == cudaSuccess;
+    ok = ok && cudaEventCreateWithFlags(&pl.ev_ready, cudaEventDisableTiming) == cudaSuccess &&
+         cudaEventCreate(&pl.ev_tail0) == cudaSuccess && cudaEventCreate(&pl.ev_tail1) == cudaSuccess &&
+         cudaEventCreate(&pl.ev_post0) == cudaSuccess && cudaEventCreate(&pl.ev_post1) == cudaSuccess;
+    ok = ok && cudaMallocHost((void **)&pl.h_count, 4 * sizeof(int)) == cudaSuccess;
     ok = ok && cudaMallocHost((void **)&ctx->h_counters, sizeof(ns_counters)) == cudaSuccess;
     ok = ok && cudaHostAlloc((void **)&ctx->h_started, sizeof(int), cudaHostAllocMapped) == cudaSuccess &&
          cudaHostGetDevicePointer((void **)&ctx->d_started, ctx->h_started, 0) == cudaSuccess;
@@ -213,14 +241,20 @@ ns_ctx *ns_create(int device, char *err, size_t errlen)
     if (!ok) {
         if (err && errlen)
             snprintf(err, errlen, "ns_create: CUDA resource creation failed: %s", cudaGetErrorString(cudaGetLastError()));
-        delete ctx;
+        ns_destroy(ctx); /* releases whatever was created */
         return nullptr;
     }
     ctx->stream = ctx->own_stream;
-    memset(&ctx->tm, 0, sizeof(ctx->tm));
     const char *cu = getenv("NS_CHUNK_UNITS");
-    if (cu)
-        ctx->chunk_units = atoll(cu);
+    if (cu) {
+        /* whole positions only (the streaming gate takes one warp per position), at least one */
+        int64_t v = atoll(cu);
+        v -= v % 3;
+        ctx->chunk_units = v < 3 ? 3 : v;
+    }
+    const char *ep = getenv("NS_POOL");
+    if (ep && atoi(ep) == 0)
+        pl.enabled = false;
     return ctx;
 }
 
@@ -233,8 +267,10 @@ void ns_destroy(ns_ctx *ctx)
     for (int i = 0; i < 2; i++) {
         ctx->in_counts[i].release();
         ctx->in_ref[i].release();
-        cudaEventDestroy(ctx->ev_h2d[i]);
-        cudaEventDestroy(ctx->ev_free[i]);
+        if (ctx->ev_h2d[i])
+            cudaEventDestroy(ctx->ev_h2d[i]);
+        if (ctx->ev_free[i])
+            cudaEventDestroy(ctx->ev_free[i]);
     }
     for (int i = 0; i < 5; i++)
         ctx->in_rows[i].release();
@@ -247,16 +283,44 @@ void ns_destroy(ns_ctx *ctx)
     ctx->fit_list.release(), ctx->post_list.release(), ctx->heavy_list.release(), ctx->pre_list.release(), ctx->emit_index_out.release(), ctx->emit_unit.release();
     ctx->counters.release(), ctx->cub_tmp.release(), ctx->rows.release(), ctx->packed.release();
     ctx->pair_idx.release(), ctx->role.release(), ctx->qtabN.release(), ctx->qtabT.release();
+    HeavyPool &pl = ctx->pool;
+    for (int i = 0; i < 5; i++)
+        pl.rows[i].release();
+    pl.is_indel.release(), pl.flags.release(), pl.iters.release(), pl.cycles.release(), pl.sigma.release(), pl.slope.release();
+    pl.max_gq.release(), pl.unit.release(), pl.lightpos.release(), pl.ident.release(), pl.emitflag.release(), pl.cnt.release();
+    pl.planes.release();
+    pl.h_rows.release();
+    if (pl.h_units)
+        cudaFreeHost(pl.h_units);
+    if (pl.h_count)
+        cudaFreeHost(pl.h_count);
+    for (int i = 0; i < NS_POOL_STREAMS; i++) {
+        if (pl.streams[i])
+            cudaStreamDestroy(pl.streams[i]);
+        if (pl.ev_done[i])
+            cudaEventDestroy(pl.ev_done[i]);
+        if (pl.ev_t0[i])
+            cudaEventDestroy(pl.ev_t0[i]);
+        if (pl.ev_t1[i])
+            cudaEventDestroy(pl.ev_t1[i]);
+    }
+    cudaEvent_t pev[] = {pl.ev_ready, pl.ev_tail0, pl.ev_tail1, pl.ev_post0, pl.ev_post1, ctx->ev_fork, ctx->ev_join, ctx->ev_h0, ctx->ev_h1};
+    for (cudaEvent_t e : pev)
+        if (e)
+            cudaEventDestroy(e);
     for (int i = 0; i < 10; i++)
-        cudaEventDestroy(ctx->ev[i]);
+        if (ctx->ev[i])
+            cudaEventDestroy(ctx->ev[i]);
     if (ctx->h_counters)
         cudaFreeHost(ctx->h_counters);
     if (ctx->h_started)
         cudaFreeHost(ctx->h_started);
-    cudaStreamDestroy(ctx->own_stream);
-    cudaStreamDestroy(ctx->copy_stream);
-    cudaStreamDestroy(ctx->heavy_stream);
-    cudaEventDestroy(ctx->ev_fork), cudaEventDestroy(ctx->ev_join), cudaEventDestroy(ctx->ev_h0), cudaEventDestroy(ctx->ev_h1);
+    if (ctx->own_stream)
+        cudaStreamDestroy(ctx->own_stream);
+    if (ctx->copy_stream)
+        cudaStreamDestroy(ctx->copy_stream);
+    if (ctx->heavy_stream)
+        cudaStreamDestroy(ctx->heavy_stream);
     delete ctx;
 }
 
@@ -273,7 +337,8 @@ int ns_set_stream(ns_ctx *ctx, void *cuda_stream)
 void *ns_alloc_pinned(size_t bytes)
 {
     void *p = nullptr;
-    if (cudaMallocHost(&p, bytes) != cudaSuccess)
+    /* portable: page-locked for every device of the process (a multi-GPU call copies from one host buffer) */
+    if (cudaHostAlloc(&p, bytes, cudaHostAllocPortable) != cudaSuccess)
         return nullptr;
     return p;
 }
@@ -320,7 +385,7 @@ int ns_measure_fp64_peak(ns_ctx *ctx, double *tflops)
 } /* extern "C" */
 
 /* upload pair index sets, build the role array and the y* tables; returns device params */
-static int ns_prepare_params(ns_ctx *ctx, const ns_params *in, int n, ns_params *dprm, const double **qtab)
+int ns_prepare_params(ns_ctx *ctx, const ns_params *in, int n, ns_params *dprm, const double **qtab)
 {
     *dprm = *in;
     if (in->n_ai_sig_tukey < 3 || in->n_ai_sig_tukey > NS_MAX_KNOTS) {
@@ -438,20 +503,24 @@ static size_t ns_heavy_smem(int n, int threads)
     return (NS_RTAB_HEAVY + ns_work_doubles(n) + (size_t)(threads / 32) * NS_COOP_DOUBLES) * sizeof(double);
 }
 
-/* cluster launch of k_fit_heavy: CL CTAs per unit, as many clusters as can be co-resident */
-static cudaError_t ns_launch_heavy(ns_ctx *ctx, cudaStream_t st, int n, int n_units_max, const ns_unit_src &src,
-                                   const ns_params &dprm, int64_t u0, const ns_unit_arrays &ua, int which,
-                                   int *n_clusters_out)
+/* cluster launch of k_fit_heavy: CL CTAs per unit, as many clusters as can be co-resident (at most max_clusters
+ * when > 0).  cp: the counter block holding this launch's unit count and list cursor. */
+static int ns_launch_heavy(ns_ctx *ctx, cudaStream_t st, int n, int n_units_max, const ns_unit_src &src,
+                           const ns_params &dprm, int64_t u0, const ns_unit_arrays &ua, ns_counters *cp, int which,
+                           int *started, int max_clusters, int *n_clusters_out)
 {
     int threads, cl;
     ns_heavy_geometry(n, n_units_max, ctx->sm_count, &threads, &cl);
     const size_t smh = ns_heavy_smem(n, threads);
-    auto kern = threads == NS_HEAVY_THREADS_TP ? k_fit_heavy_tp : k_fit_heavy;
-    cudaError_t e;
-    if (smh > 48 * 1024 && (e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smh)))
-        return e;
-    if (cl > 8 && (e = cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1)))
-        return e;
+    if (smh > 227 * 1024) {
+        ctx->err = "too many samples for the cluster kernel's working set";
+        return NS_ERR_ARG;
+    }
+    const bool tp = threads == NS_HEAVY_THREADS_TP;
+    auto kern = tp ? k_fit_heavy_tp : k_fit_heavy;
+    CK(ns_need_smem(ctx, tp ? 1 : 0, kern, smh));
+    if (cl > 8)
+        CK(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
     cudaLaunchConfig_t cfg = {};
     cfg.blockDim = dim3(threads);
     cfg.dynamicSmemBytes = smh;
@@ -465,19 +534,19 @@ static cudaError_t ns_launch_heavy(ns_ctx *ctx, cudaStream_t st, int n, int n_un
     cfg.numAttrs = 1;
     cfg.gridDim = dim3(cl);
     int ncl = 0;
-    e = cudaOccupancyMaxActiveClusters(&ncl, kern, &cfg);
-    if (e != cudaSuccess)
-        return e;
+    CK(cudaOccupancyMaxActiveClusters(&ncl, kern, &cfg));
     if (ncl < 1)
         ncl = 1;
     if (ncl > n_units_max)
         ncl = n_units_max;
+    if (max_clusters > 0 && ncl > max_clusters)
+        ncl = max_clusters;
     cfg.gridDim = dim3(cl * ncl);
-    ns_counters *cp = ctx->counters.p;
-    int *started = which == 0 ? ctx->d_started : nullptr;
     if (n_clusters_out)
         *n_clusters_out = ncl;
-    return cudaLaunchKernelEx(&cfg, kern, src, dprm, u0, ua, cp, which, started);
+    CK(cudaLaunchKernelEx(&cfg, kern, src, dprm, u0, ua, cp, which, started));
+    ctx->tm.kernel_launches++;
+    return NS_OK;
 }
 
 static float ev_ms(cudaEvent_t a, cudaEvent_t b)
@@ -487,12 +556,319 @@ static float ev_ms(cudaEvent_t a, cudaEvent_t b)
     return ms;
 }
 
+/* ---- call-wide pool of cluster-path units --------------------------------------------------------- */
+static int ns_pool_begin(ns_ctx *ctx, int n)
+{
+    HeavyPool &pl = ctx->pool;
+    pl.n_used = pl.n_launch = 0;
+    pl.next_stream = 0;
+    for (int i = 0; i < NS_POOL_STREAMS; i++)
+        pl.used[i] = false;
+    if (!pl.enabled)
+        return NS_OK;
+    /* ~80 B per sample per pooled unit (count rows + result planes): 8192 units up to n = 400, fewer beyond */
+    int cap = (int)std::min<double>(8192.0, 256.0e6 / (80.0 * n));
+    const char *ec = getenv("NS_POOL_CAP");
+    if (ec && atoi(ec) > 0)
+        cap = atoi(ec);
+    if (cap < 16)
+        cap = 16;
+    if (pl.cap == cap && pl.n == n)
+        return NS_OK;
+    const size_t m = (size_t)cap * n;
+    cudaError_t e = cudaSuccess;
+    for (int k = 0; k < 5 && e == cudaSuccess; k++)
+        e = pl.rows[k].reserve(m);
+    if (e || (e = pl.is_indel.reserve(cap)) || (e = pl.flags.reserve(cap)) || (e = pl.iters.reserve(cap)) ||
+        (e = pl.cycles.reserve(cap)) || (e = pl.sigma.reserve(cap)) || (e = pl.slope.reserve(cap)) ||
+        (e = pl.max_gq.reserve(cap)) || (e = pl.unit.reserve(cap)) || (e = pl.lightpos.reserve(cap)) ||
+        (e = pl.ident.reserve(cap)) || (e = pl.emitflag.reserve(cap)) || (e = pl.cnt.reserve(NS_POOL_MAX_LAUNCH + 1)) ||
+        (e = pl.planes.reserve(cap, n))) {
+        ctx->err = std::string("device allocation (cluster-path pool) failed: ") + cudaGetErrorString(e);
+        return NS_ERR_NOMEM;
+    }
+    std::vector<int> id((size_t)cap);
+    for (int i = 0; i < cap; i++)
+        id[i] = i;
+    CK(cudaMemcpyAsync(pl.ident.p, id.data(), (size_t)cap * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    pl.cap = cap;
+    pl.n = n;
+    return NS_OK;
+}
+
+static ns_pool_dev ns_pool_view(HeavyPool &pl)
+{
+    ns_pool_dev v = {pl.rows[0].p, pl.rows[1].p, pl.rows[2].p, pl.rows[3].p, pl.rows[4].p,
+                     pl.is_indel.p, pl.flags.p, pl.unit.p, pl.lightpos.p};
+    return v;
+}
+
+static ns_unit_src ns_pool_src(HeavyPool &pl, int n, int plain)
+{
+    ns_unit_src s;
+    memset(&s, 0, sizeof(s));
+    s.mode = 1;
+    s.n = n;
+    s.dp = pl.rows[0].p, s.vp = pl.rows[1].p, s.vm = pl.rows[2].p, s.rp = pl.rows[3].p, s.rm = pl.rows[4].p;
+    s.is_indel = pl.is_indel.p;
+    s.plain = plain;
+    return s;
+}
+
+/* unit arrays of the pool: "unit" = pool slot; the lists are slices of the identity */
+static ns_unit_arrays ns_pool_ua(HeavyPool &pl, int first)
+{
+    ns_unit_arrays ua = {pl.flags.p, pl.iters.p, pl.cycles.p, pl.sigma.p, pl.slope.p, pl.max_gq.p, pl.emitflag.p,
+                         pl.ident.p, pl.emitflag.p, pl.emitflag.p, pl.ident.p, pl.ident.p, pl.ident.p, pl.ident.p + first};
+    return ua;
+}
+
+/* can `count` more units of this chunk go to the pool? */
+static bool ns_pool_room(ns_ctx *ctx, int count)
+{
+    HeavyPool &pl = ctx->pool;
+    int max_per_chunk = 1024; /* beyond this the chunk is a deep panel: the in-chunk throughput regime is the better fit */
+    const char *em = getenv("NS_POOL_MAX_PER_CHUNK");
+    if (em && atoi(em) > 0)
+        max_per_chunk = atoi(em);
+    return pl.enabled && pl.cap > 0 && count > 0 && count <= max_per_chunk && pl.n_used + count <= pl.cap &&
+           pl.n_launch < NS_POOL_MAX_LAUNCH;
+}
+
+/* moves `count` units of the current chunk (listed in `list`) into the pool and starts the cluster kernel for them on
+ * one of the pool's streams; wait_resident: let the clusters take their SMs before the caller launches k_fit */
+static int ns_pool_submit(ns_ctx *ctx, const ns_params &dprm, const ns_unit_src &src, int64_t u0_src, int64_t u_off,
+                          const int *list, int count, const ns_unit_arrays &ua, bool wait_resident)
+{
+    HeavyPool &pl = ctx->pool;
+    const int n = src.n;
+    cudaStream_t st = ctx->stream;
+    const int base = pl.n_used, k = pl.n_launch;
+    {
+        const int wpb = 8;
+        int blocks = (count + wpb - 1) / wpb;
+        if (blocks > ctx->sm_count * 4)
+            blocks = ctx->sm_count * 4;
+        k_pool_gather<<<blocks, wpb * 32, 0, st>>>(src, u0_src, u_off, list, count, ua, ns_pool_view(pl), base, pl.cnt.p + k);
+        CK(cudaGetLastError());
+        ctx->tm.kernel_launches++;
+    }
+    CK(cudaEventRecord(pl.ev_ready, st));
+    const int si = pl.next_stream;
+    pl.next_stream = (pl.next_stream + 1) % NS_POOL_STREAMS;
+    cudaStream_t hs = pl.streams[si];
+    CK(cudaStreamWaitEvent(hs, pl.ev_ready, 0));
+    if (!pl.used[si]) {
+        CK(cudaEventRecord(pl.ev_t0[si], hs));
+        pl.used[si] = true;
+    }
+    int ncl = 0, max_cl = 0;
+    const char *emc = getenv("NS_POOL_MAX_CLUSTERS");
+    if (emc && atoi(emc) > 0)
+        max_cl = atoi(emc);
+    int *started = wait_resident ? ctx->d_started : nullptr;
+    if (wait_resident)
+        *(volatile int *)ctx->h_started = 0;
+    int rc = ns_launch_heavy(ctx, hs, n, count, ns_pool_src(pl, n, src.plain), dprm, 0, ns_pool_ua(pl, base), pl.cnt.p + k, 0,
+                             started, max_cl, &ncl);
+    if (rc)
+        return rc;
+    CK(cudaEventRecord(pl.ev_t1[si], hs));
+    if (wait_resident) {
+        /* a cluster needs whole SMs and the persistent warp kernel would never give them back: bounded host-side
+         * wait on a mapped flag until the clusters are resident (not a kernel waiting on a kernel) */
+        const auto t0 = std::chrono::steady_clock::now();
+        while (*(volatile int *)ctx->h_started < ncl) {
+            if (std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() > 0.02)
+                break;
+        }
+    }
+    pl.n_used += count;
+    pl.n_launch++;
+    return NS_OK;
+}
+
+/* end of the call: join the pool's streams, run k_post for the pooled units, bring their results to the host and
+ * merge them into the per-unit arrays and the emitted rows (which stay in unit order) */
+static int ns_pool_finish(ns_ctx *ctx, const ns_params &dprm, const double *qtab, int n, int plain, ns_out *out,
+                          RowSink *sink, int64_t *emit_off, int64_t n_units_total)
+{
+    HeavyPool &pl = ctx->pool;
+    if (pl.n_used == 0)
+        return NS_OK;
+    cudaStream_t st = ctx->stream;
+    const int M = pl.n_used;
+    CK(cudaEventRecord(pl.ev_tail0, st));
+    for (int i = 0; i < NS_POOL_STREAMS; i++)
+        if (pl.used[i]) {
+            CK(cudaEventRecord(pl.ev_done[i], pl.streams[i]));
+            CK(cudaStreamWaitEvent(st, pl.ev_done[i], 0));
+        }
+    CK(cudaEventRecord(pl.ev_tail1, st));
+    /* k_post over the pool slots */
+    ns_counters *pc = pl.cnt.p + NS_POOL_MAX_LAUNCH;
+    CK(cudaMemsetAsync(pc, 0, sizeof(ns_counters), st));
+    pl.h_count[0] = M;
+    CK(cudaMemcpyAsync(&pc->n_post, &pl.h_count[0], sizeof(int), cudaMemcpyHostToDevice, st));
+    CK(cudaMemsetAsync(pl.emitflag.p, 0, (size_t)M * sizeof(int), st));
+    CK(cudaEventRecord(pl.ev_post0, st));
+    {
+        int wpb = 4;
+        size_t per_warp = (3 * (size_t)n + 8) * sizeof(double);
+        while (wpb > 1 && wpb * per_warp > 200 * 1024)
+            wpb >>= 1;
+        size_t sm = NS_RTAB * sizeof(double) + wpb * per_warp;
+        CK(ns_need_smem(ctx, 3, k_post, sm));
+        int blocks = (M + wpb - 1) / wpb;
+        if (blocks > ctx->sm_count * 4)
+            blocks = ctx->sm_count * 4;
+        k_post<<<blocks, wpb * 32, sm, st>>>(ns_pool_src(pl, n, plain), dprm, 0, ns_pool_ua(pl, 0), pl.planes.view(), qtab,
+                                            NS_QTAB_LEN, pc);
+        CK(cudaGetLastError());
+        ctx->tm.kernel_launches++;
+    }
+    CK(cudaEventRecord(pl.ev_post1, st));
+    /* per-unit results and the launches' work counters */
+    const size_t per_unit = sizeof(int64_t) * 2 + sizeof(double) * 3 + sizeof(uint32_t) * 2 + sizeof(unsigned long long) + sizeof(int);
+    const size_t need = (size_t)M * per_unit + (size_t)(NS_POOL_MAX_LAUNCH + 1) * sizeof(ns_counters) + 256;
+    if (need > pl.h_units_cap) {
+        if (pl.h_units)
+            cudaFreeHost(pl.h_units);
+        pl.h_units = nullptr;
+        pl.h_units_cap = 0;
+        if (cudaMallocHost((void **)&pl.h_units, need * 2) != cudaSuccess) {
+            ctx->err = "page-locked allocation (pool staging) failed";
+            return NS_ERR_NOMEM;
+        }
+        pl.h_units_cap = need * 2;
+    }
+    char *hp = pl.h_units;
+    int64_t *h_unit = (int64_t *)hp;
+    hp += (size_t)M * sizeof(int64_t);
+    int64_t *h_lightpos = (int64_t *)hp;
+    hp += (size_t)M * sizeof(int64_t);
+    double *h_sigma = (double *)hp;
+    hp += (size_t)M * sizeof(double);
+    double *h_slope = (double *)hp;
+    hp += (size_t)M * sizeof(double);
+    double *h_maxgq = (double *)hp;
+    hp += (size_t)M * sizeof(double);
+    unsigned long long *h_cycles = (unsigned long long *)hp;
+    hp += (size_t)M * sizeof(unsigned long long);
+    ns_counters *h_cnt = (ns_counters *)hp;
+    hp += (size_t)(NS_POOL_MAX_LAUNCH + 1) * sizeof(ns_counters);
+    uint32_t *h_flags = (uint32_t *)hp;
+    hp += (size_t)M * sizeof(uint32_t);
+    uint32_t *h_iters = (uint32_t *)hp;
+    hp += (size_t)M * sizeof(uint32_t);
+    int *h_emit = (int *)hp;
+#define PD2H(dst, srcp, count, type) CK(cudaMemcpyAsync((dst), (srcp), (size_t)(count) * sizeof(type), cudaMemcpyDeviceToHost, st))
+    PD2H(h_unit, pl.unit.p, M, int64_t);
+    PD2H(h_lightpos, pl.lightpos.p, M, int64_t);
+    PD2H(h_sigma, pl.sigma.p, M, double);
+    PD2H(h_slope, pl.slope.p, M, double);
+    PD2H(h_maxgq, pl.max_gq.p, M, double);
+    PD2H(h_cycles, pl.cycles.p, M, unsigned long long);
+    PD2H(h_cnt, pl.cnt.p, pl.n_launch, ns_counters);
+    PD2H(h_flags, pl.flags.p, M, uint32_t);
+    PD2H(h_iters, pl.iters.p, M, uint32_t);
+    PD2H(h_emit, pl.emitflag.p, M, int);
+    if (sink->want_rows) {
+        if (!pl.h_rows.reserve(M, n, 0)) {
+            ctx->err = "page-locked allocation (pool rows) failed";
+            return NS_ERR_NOMEM;
+        }
+        const size_t m = (size_t)M * n;
+        ns_planes pk = pl.planes.view();
+        const ns_row_planes &h = pl.h_rows.p;
+        if (sink->p.pvalue)
+            PD2H(h.pvalue, pk.pvalue, m, double);
+        if (sink->p.qvalue)
+            PD2H(h.qvalue, pk.qvalue, m, double);
+        if (sink->p.gq)
+            PD2H(h.gq, pk.gq, m, double);
+        if (sink->p.qval_minaf)
+            PD2H(h.qval_minaf, pk.qval_minaf, m, double);
+        if (sink->p.sor)
+            PD2H(h.sor, pk.sor, m, double);
+        if (sink->p.rvsb)
+            PD2H(h.rvsb, pk.rvsb, m, double);
+        if (sink->p.fs)
+            PD2H(h.fs, pk.fs, m, double);
+        if (sink->p.gt)
+            PD2H(h.gt, pk.gt, m, uint8_t);
+        if (sink->p.status)
+            PD2H(h.status, pk.status, m, uint8_t);
+        if (sink->p.pooled)
+            PD2H(h.pooled, pk.pooled, (size_t)M * 8, double);
+    }
+#undef PD2H
+    CK(cudaStreamSynchronize(st));
+    for (int i = 0; i < NS_POOL_STREAMS; i++)
+        if (pl.used[i])
+            ctx->tm.heavy_pre_ms += ev_ms(pl.ev_t0[i], pl.ev_t1[i]);
+    ctx->tm.pool_tail_ms += ev_ms(pl.ev_tail0, pl.ev_tail1);
+    ctx->tm.post_ms += ev_ms(pl.ev_post0, pl.ev_post1);
+    ctx->tm.pool_units += M;
+    for (int k = 0; k < pl.n_launch; k++) {
+        out->n_seed += h_cnt[k].n_seed;
+        out->n_lattice += h_cnt[k].n_lattice;
+        out->n_quad += h_cnt[k].n_quad;
+    }
+    /* per-unit arrays */
+    for (int i = 0; i < M; i++) {
+        const int64_t u = h_unit[i];
+        if (out->sigma)
+            out->sigma[u] = h_sigma[i];
+        if (out->slope)
+            out->slope[u] = h_slope[i];
+        if (out->max_gq)
+            out->max_gq[u] = h_maxgq[i];
+        if (out->flags)
+            out->flags[u] = h_flags[i] & ~NS_F_POOLED;
+        if (out->iters)
+            out->iters[u] = h_iters[i];
+        if (out->unit_cycles)
+            out->unit_cycles[u] = h_cycles[i];
+    }
+    /* emitted rows: the pooled units that emit, in unit order, each with the number of rows that precede it */
+    std::vector<ns_late_row> late;
+    for (int i = 0; i < M; i++)
+        if (h_emit[i])
+            late.push_back(ns_late_row{h_unit[i], h_lightpos[i], (int64_t)i});
+    std::sort(late.begin(), late.end(), [](const ns_late_row &a, const ns_late_row &b) { return a.unit < b.unit; });
+    const int64_t E1 = *emit_off, E2 = (int64_t)late.size();
+    if (E2 > 0) {
+        if (sink->grow && E1 + E2 > sink->cap) {
+            if (!sink->grow->reserve(E1 + E2, n, E1)) {
+                ctx->err = "page-locked allocation (emitted rows) failed";
+                return NS_ERR_NOMEM;
+            }
+            sink->p = sink->grow->p;
+            sink->cap = sink->grow->cap;
+        }
+        if (E1 + E2 <= sink->cap || !sink->want_rows) {
+            ns_row_planes dst = sink->p;
+            if (!sink->want_rows)
+                memset(&dst, 0, sizeof(dst));
+            ns_merge_pool_rows(dst, E1, pl.h_rows.p, late.data(), E2, n, out->emit_index, n_units_total);
+        }
+        *emit_off = E1 + E2;
+    }
+    pl.n_used = pl.n_launch = 0;
+    for (int i = 0; i < NS_POOL_STREAMS; i++)
+        pl.used[i] = false;
+    return NS_OK;
+}
+
 /* one chunk of units whose inputs are on the device; results to host at unit offset u_off */
 static int ns_run_chunk(ns_ctx *ctx, const ns_params &dprm, const double *qtab, const ns_unit_src &src, int64_t u0_src,
-                        int64_t u_off, int U, ns_out *out, int64_t *emit_off)
+                        int64_t u_off, int U, ns_out *out, RowSink *sink, int64_t *emit_off)
 {
     const int n = src.n;
     cudaStream_t st = ctx->stream;
+    HeavyPool &pl = ctx->pool;
     cudaError_t ce = ns_reserve_units(ctx, (size_t)U);
     if (ce != cudaSuccess) {
         ctx->err = std::string("device allocation (unit arrays) failed: ") + cudaGetErrorString(ce);
@@ -509,8 +885,7 @@ static int ns_run_chunk(ns_ctx *ctx, const ns_params &dprm, const double *qtab, 
         if (blocks > maxb)
             blocks = maxb;
         size_t sm = (size_t)NS_WPB_GATE * n * sizeof(double);
-        if (sm > 48 * 1024)
-            CK(cudaFuncSetAttribute(k_gate, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+        CK(ns_need_smem(ctx, 2, k_gate, sm));
         k_gate<<<blocks, NS_WPB_GATE * 32, sm, st>>>(src, dprm, u0_src, U, ua, ctx->counters.p);
         CK(cudaGetLastError());
     }
@@ -530,29 +905,27 @@ static int ns_run_chunk(ns_ctx *ctx, const ns_params &dprm, const double *qtab, 
         ctx->err = std::string("device allocation (result planes) failed: ") + cudaGetErrorString(ce);
         return NS_ERR_NOMEM;
     }
-    /* fit: the CTA-per-unit kernel for the units predicted heavy runs on its own stream next to
-     * the persistent warp kernel; units the warp kernel hands over later get a second pass */
+    /* fit.  Units predicted for the cluster kernel: into the call-wide pool when it has room (they then run next to
+     * this and later chunks and are joined at the end of the call), else - deep panels, where every unit is one - on
+     * the side stream within this chunk.  Units the warp kernel hands over go the same two ways. */
     const int n_pre = ctx->h_counters->n_pre, n_light = ctx->h_counters->n_light;
     CK(cudaEventRecord(ctx->ev[2], st));
     bool heavy_forked = false;
-    if (n_fit > 0) {
-        int hth, hcl;
-        ns_heavy_geometry(n, 1, ctx->sm_count, &hth, &hcl);
-        if (ns_heavy_smem(n, hth) > 227 * 1024) {
-            ctx->err = "too many samples for the heavy kernel's working set";
-            return NS_ERR_ARG;
-        }
-    }
-    if (n_pre > 0) {
+    int n_pooled = 0;
+    if (n_pre > 0 && ns_pool_room(ctx, n_pre)) {
+        int rc = ns_pool_submit(ctx, dprm, src, u0_src, u_off, ctx->pre_list.p, n_pre, ua, n_light > 0);
+        if (rc)
+            return rc;
+        n_pooled += n_pre;
+    } else if (n_pre > 0) {
         CK(cudaEventRecord(ctx->ev_fork, st));
         CK(cudaStreamWaitEvent(ctx->heavy_stream, ctx->ev_fork, 0));
         CK(cudaEventRecord(ctx->ev_h0, ctx->heavy_stream));
         int ncl = 0;
         *(volatile int *)ctx->h_started = 0;
-        CK(ns_launch_heavy(ctx, ctx->heavy_stream, n, n_pre, src, dprm, u0_src, ua, 0, &ncl));
-        /* Let the clusters take their SMs before the persistent warp kernel fills the machine: a
-         * cluster needs whole SMs, the warp kernel's CTAs would never give them back.  Host-side
-         * wait on a mapped flag (bounded), not a kernel waiting on a kernel. */
+        int rc = ns_launch_heavy(ctx, ctx->heavy_stream, n, n_pre, src, dprm, u0_src, ua, ctx->counters.p, 0, ctx->d_started, 0, &ncl);
+        if (rc)
+            return rc;
         if (n_light > 0) {
             const auto t0 = std::chrono::steady_clock::now();
             while (*(volatile int *)ctx->h_started < ncl) {
@@ -563,7 +936,6 @@ static int ns_run_chunk(ns_ctx *ctx, const ns_params &dprm, const double *qtab, 
         CK(cudaEventRecord(ctx->ev_h1, ctx->heavy_stream));
         CK(cudaEventRecord(ctx->ev_join, ctx->heavy_stream));
         heavy_forked = true;
-        ctx->tm.kernel_launches++;
     }
     if (n_light > 0) {
         const int wpb = 4;
@@ -573,8 +945,7 @@ static int ns_run_chunk(ns_ctx *ctx, const ns_params &dprm, const double *qtab, 
             ctx->err = "too many samples for the on-chip working set (n > ~1100)";
             return NS_ERR_ARG;
         }
-        if (sm > 48 * 1024)
-            CK(cudaFuncSetAttribute(k_fit, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+        CK(ns_need_smem(ctx, 4, k_fit, sm));
         int bps = 0;
         CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_fit, wpb * 32, sm));
         if (bps < 1)
@@ -590,14 +961,21 @@ static int ns_run_chunk(ns_ctx *ctx, const ns_params &dprm, const double *qtab, 
     CK(cudaEventRecord(ctx->ev[7], st));
     if (heavy_forked)
         CK(cudaStreamWaitEvent(st, ctx->ev_join, 0));
+    int n_def = 0;
     if (n_light > 0) {
-        /* units the warp kernel handed over (rare): read their count, launch only if there are any */
+        /* units the warp kernel handed over (rare): read their count, act only if there are any */
         CK(cudaMemcpyAsync(&ctx->h_counters->n_heavy, &ctx->counters.p->n_heavy, sizeof(int), cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
-        const int n_def = ctx->h_counters->n_heavy;
-        if (n_def > 0) {
-            CK(ns_launch_heavy(ctx, st, n, n_def, src, dprm, u0_src, ua, 1, nullptr));
-            ctx->tm.kernel_launches++;
+        n_def = ctx->h_counters->n_heavy;
+        if (n_def > 0 && ns_pool_room(ctx, n_def)) {
+            int rc = ns_pool_submit(ctx, dprm, src, u0_src, u_off, ctx->heavy_list.p, n_def, ua, false);
+            if (rc)
+                return rc;
+            n_pooled += n_def;
+        } else if (n_def > 0) {
+            int rc = ns_launch_heavy(ctx, st, n, n_def, src, dprm, u0_src, ua, ctx->counters.p, 1, nullptr, 0, nullptr);
+            if (rc)
+                return rc;
         }
     }
     CK(cudaEventRecord(ctx->ev[3], st));
@@ -609,8 +987,7 @@ static int ns_run_chunk(ns_ctx *ctx, const ns_params &dprm, const double *qtab, 
         while (wpb > 1 && wpb * per_warp > 200 * 1024)
             wpb >>= 1;
         size_t sm = NS_RTAB * sizeof(double) + wpb * per_warp;
-        if (sm > 48 * 1024)
-            CK(cudaFuncSetAttribute(k_post, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+        CK(ns_need_smem(ctx, 3, k_post, sm));
         int bps = 0;
         CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_post, wpb * 32, sm));
         if (bps < 1)
@@ -634,9 +1011,15 @@ static int ns_run_chunk(ns_ctx *ctx, const ns_params &dprm, const double *qtab, 
     CK(cudaMemcpyAsync(ctx->h_counters, ctx->counters.p, sizeof(ns_counters), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     const int n_emit = ctx->h_counters->n_emit;
-    const bool want_rows = out->pvalue || out->qvalue || out->gq || out->qval_minaf || out->sor || out->rvsb ||
-                           out->fs || out->gt || out->status || out->pooled || out->emit_unit;
-    int64_t room = out->emit_cap - *emit_off;
+    if (sink->grow && *emit_off + n_emit > sink->cap) {
+        if (!sink->grow->reserve(*emit_off + n_emit, n, *emit_off)) {
+            ctx->err = "page-locked allocation (emitted rows) failed";
+            return NS_ERR_NOMEM;
+        }
+        sink->p = sink->grow->p;
+        sink->cap = sink->grow->cap;
+    }
+    int64_t room = sink->cap - *emit_off;
     if (room < 0)
         room = 0;
     const int n_copy = (int)((int64_t)n_emit < room ? n_emit : room);
@@ -658,7 +1041,8 @@ static int ns_run_chunk(ns_ctx *ctx, const ns_params &dprm, const double *qtab, 
         if (blocks > ctx->sm_count * 8)
             blocks = ctx->sm_count * 8;
         k_pack<<<blocks, wpb * 32, 0, st>>>(n, U, u_off, *emit_off, (int)ctx->packed_cap, ua, ctx->rows.view(),
-                                            ctx->packed.view(), ctx->emit_unit.p, ctx->emit_index_out.p);
+                                            ctx->packed.view(), ctx->emit_unit.p, ctx->emit_index_out.p, pl.lightpos.p,
+                                            ctx->counters.p);
         CK(cudaGetLastError());
     }
     CK(cudaEventRecord(ctx->ev[5], st));
@@ -673,21 +1057,23 @@ static int ns_run_chunk(ns_ctx *ctx, const ns_params &dprm, const double *qtab, 
     D2H(out->iters ? out->iters + u_off : nullptr, ctx->iters.p, U, uint32_t);
     D2H(out->unit_cycles ? out->unit_cycles + u_off : nullptr, ctx->cycles.p, U, uint64_t);
     D2H(out->emit_index ? out->emit_index + u_off : nullptr, ctx->emit_index_out.p, U, int32_t);
-    if (want_rows && n_copy > 0) {
+    D2H(&ctx->h_counters->n_skipped, &ctx->counters.p->n_skipped, 1, int);
+    if (sink->want_rows && n_copy > 0) {
         const size_t eo = (size_t)*emit_off;
         const size_t m = (size_t)n_copy * n;
         ns_planes pk = ctx->packed.view();
-        D2H(out->pvalue ? out->pvalue + eo * n : nullptr, pk.pvalue, m, double);
-        D2H(out->qvalue ? out->qvalue + eo * n : nullptr, pk.qvalue, m, double);
-        D2H(out->gq ? out->gq + eo * n : nullptr, pk.gq, m, double);
-        D2H(out->qval_minaf ? out->qval_minaf + eo * n : nullptr, pk.qval_minaf, m, double);
-        D2H(out->sor ? out->sor + eo * n : nullptr, pk.sor, m, double);
-        D2H(out->rvsb ? out->rvsb + eo * n : nullptr, pk.rvsb, m, double);
-        D2H(out->fs ? out->fs + eo * n : nullptr, pk.fs, m, double);
-        D2H(out->gt ? out->gt + eo * n : nullptr, pk.gt, m, uint8_t);
-        D2H(out->status ? out->status + eo * n : nullptr, pk.status, m, uint8_t);
-        D2H(out->pooled ? out->pooled + eo * 8 : nullptr, pk.pooled, (size_t)n_copy * 8, double);
-        D2H(out->emit_unit ? out->emit_unit + eo : nullptr, ctx->emit_unit.p, n_copy, int64_t);
+        const ns_row_planes &sp = sink->p;
+        D2H(sp.pvalue ? sp.pvalue + eo * n : nullptr, pk.pvalue, m, double);
+        D2H(sp.qvalue ? sp.qvalue + eo * n : nullptr, pk.qvalue, m, double);
+        D2H(sp.gq ? sp.gq + eo * n : nullptr, pk.gq, m, double);
+        D2H(sp.qval_minaf ? sp.qval_minaf + eo * n : nullptr, pk.qval_minaf, m, double);
+        D2H(sp.sor ? sp.sor + eo * n : nullptr, pk.sor, m, double);
+        D2H(sp.rvsb ? sp.rvsb + eo * n : nullptr, pk.rvsb, m, double);
+        D2H(sp.fs ? sp.fs + eo * n : nullptr, pk.fs, m, double);
+        D2H(sp.gt ? sp.gt + eo * n : nullptr, pk.gt, m, uint8_t);
+        D2H(sp.status ? sp.status + eo * n : nullptr, pk.status, m, uint8_t);
+        D2H(sp.pooled ? sp.pooled + eo * 8 : nullptr, pk.pooled, (size_t)n_copy * 8, double);
+        D2H(sp.emit_unit ? sp.emit_unit + eo : nullptr, ctx->emit_unit.p, n_copy, int64_t);
     }
 #undef D2H
     CK(cudaEventRecord(ctx->ev[6], st));
@@ -698,107 +1084,72 @@ static int ns_run_chunk(ns_ctx *ctx, const ns_params &dprm, const double *qtab, 
     if (heavy_forked)
         ctx->tm.heavy_pre_ms += ev_ms(ctx->ev_h0, ctx->ev_h1);
     ctx->tm.fit_phase_ms += ev_ms(ctx->ev[2], ctx->ev[3]);
-    ctx->tm.n_heavy += ctx->h_counters->n_heavy + ctx->h_counters->n_pre;
-    ctx->tm.n_deferred += ctx->h_counters->n_heavy;
+    ctx->tm.n_heavy += n_def + n_pre;
+    ctx->tm.n_deferred += n_def;
     ctx->tm.fast_seed += ctx->h_counters->fast_seed;
     ctx->tm.fast_lattice += ctx->h_counters->fast_lattice;
     ctx->tm.post_ms += ev_ms(ctx->ev[3], ctx->ev[4]);
     ctx->tm.pack_ms += ev_ms(ctx->ev[4], ctx->ev[5]);
     ctx->tm.d2h_ms += ev_ms(ctx->ev[5], ctx->ev[6]);
     ctx->tm.kernel_launches += 8; /* gate, 2 x (cub scan = init + scan kernels, total), pack */
+    ctx->tm.chunks += 1;
+    ctx->n_skipped_call += ctx->h_counters->n_skipped;
     *emit_off += n_emit;
     out->n_fitted += n_fit;
     out->n_seed += ctx->h_counters->n_seed;
     out->n_lattice += ctx->h_counters->n_lattice;
     out->n_quad += ctx->h_counters->n_quad;
+    (void)n_pooled;
     return NS_OK;
 }
 
-static int64_t ns_pick_chunk(ns_ctx *ctx, int n, int64_t total_units)
+int64_t ns_pick_chunk(ns_ctx *ctx, int n, int64_t total_units)
 {
-    if (ctx->chunk_units > 0)
-        return ctx->chunk_units;
-    /* bound the per-chunk result planes (58 B per sample per row) to ~1.5 GB */
-    int64_t c = (int64_t)(6000.0e6 / (58.0 * n));
-    /* ~1 GB of count planes per chunk, at least 262144 positions: small panels (WGS-like, few samples) get
-     * proportionally more positions per chunk, so that the few cluster-path units of a chunk (whose critical
-     * path is tens of ms whatever the chunk holds) are amortised over more streamed positions */
-    int64_t cap = 3 * (int64_t)(0.94e9 / (36.0 * n)); /* n = 100: 262144 positions, the measured end-to-end optimum */
-    if (cap < 3 * 262144)
-        cap = 3 * 262144;
-    if (cap > 3 * 2097152)
-        cap = 3 * 2097152; /* per-unit arrays: ~70 B per unit */
-    if (c > cap)
-        c = cap;
-    if (c < 3 * 256)
-        c = 3 * 256;
+    int64_t c;
+    if (ctx->chunk_units > 0) {
+        c = ctx->chunk_units;
+    } else {
+        /* bound the per-chunk result planes (58 B per sample per row, twice with the packed copy): <= ~6 GB */
+        c = (int64_t)(6000.0e6 / (58.0 * n));
+        /* ~1 GB of count planes per chunk, at least 262144 positions: small panels (WGS-like, few samples) get
+         * proportionally more positions per chunk */
+        int64_t cap = 3 * (int64_t)(0.94e9 / (36.0 * n)); /* n = 100: 262144 positions, the measured end-to-end optimum */
+        if (cap < 3 * 262144)
+            cap = 3 * 262144;
+        if (cap > 3 * 2097152)
+            cap = 3 * 2097152; /* per-unit arrays: ~70 B per unit */
+        if (c > cap)
+            c = cap;
+        if (c < 3 * 256)
+            c = 3 * 256;
+    }
     c -= c % 3;
+    if (c < 3)
+        c = 3;
     if (c > total_units)
         c = total_units;
     return c;
 }
 
-static void ns_reset_out(ns_ctx *ctx, ns_out *out)
+void ns_reset_out(ns_ctx *ctx, ns_out *out)
 {
     out->n_emitted = 0;
     out->n_fitted = out->n_gated = out->n_skipped = 0;
     out->n_seed = out->n_lattice = out->n_quad = 0;
     memset(&ctx->tm, 0, sizeof(ctx->tm));
+    ctx->n_skipped_call = 0;
 }
 
-static void ns_finish_out(ns_out *out, int64_t total_units, int64_t emitted)
+static void ns_finish_out(ns_ctx *ctx, ns_out *out, int64_t total_units, int64_t emitted)
 {
     out->n_emitted = emitted;
-    out->n_gated = total_units - out->n_fitted;
-    if (out->flags) {
-        int64_t sk = 0;
-        for (int64_t u = 0; u < total_units; u++)
-            sk += (out->flags[u] & NS_F_SKIPPED) != 0;
-        out->n_skipped = sk;
-        out->n_gated -= sk;
-    }
+    out->n_skipped = ctx->n_skipped_call; /* counted on the device (k_pack), not by a host pass over the flags */
+    out->n_gated = total_units - out->n_fitted - out->n_skipped;
 }
 
-extern "C" {
-
-int ns_call_snv_device(ns_ctx *ctx, const ns_params *prm, int n, int64_t P, const uint8_t *d_ref,
-                       const int32_t *d_counts, ns_out *out)
+static int ns_check_overflow(ns_ctx *ctx, ns_out *out, int64_t emitted)
 {
-    if (!ctx)
-        return NS_ERR_ARG;
-    if (!prm || !out || n < 1 || P < 0 || (P > 0 && (!d_ref || !d_counts))) {
-        ctx->err = "ns_call_snv_device: bad argument";
-        return NS_ERR_ARG;
-    }
-    CK(cudaSetDevice(ctx->device));
-    ns_reset_out(ctx, out);
-    ns_params dprm;
-    const double *qtab = nullptr;
-    int rc = ns_prepare_params(ctx, prm, n, &dprm, &qtab);
-    if (rc)
-        return rc;
-    cudaEvent_t t0 = ctx->ev[8], t1 = ctx->ev[9];
-    CK(cudaEventRecord(t0, ctx->stream));
-    const int64_t U = 3 * P;
-    const int64_t chunk = U > 0 ? ns_pick_chunk(ctx, n, U) : 0;
-    int64_t emit_off = 0;
-    ns_unit_src src;
-    memset(&src, 0, sizeof(src));
-    src.mode = 0;
-    src.n = n;
-    src.counts = d_counts;
-    src.ref = d_ref;
-    for (int64_t u0 = 0; u0 < U; u0 += chunk) {
-        int Uc = (int)((U - u0 < chunk) ? (U - u0) : chunk);
-        rc = ns_run_chunk(ctx, dprm, qtab, src, u0, u0, Uc, out, &emit_off);
-        if (rc)
-            return rc;
-    }
-    CK(cudaEventRecord(t1, ctx->stream));
-    CK(cudaEventSynchronize(t1));
-    ctx->tm.total_ms = ev_ms(t0, t1);
-    ns_finish_out(out, U, emit_off);
-    if (emit_off > out->emit_cap && (out->pvalue || out->gq || out->emit_unit)) {
+    if (emitted > out->emit_cap && (out->pvalue || out->gq || out->emit_unit)) {
         ctx->err = "more emitted units than out->emit_cap";
         return NS_ERR_EMIT_OVERFLOW;
     }
@@ -821,15 +1172,9 @@ __global__ void k_widen16(const uint16_t *__restrict__ src, int32_t *__restrict_
         dst[i] = (int32_t)src[i];
 }
 
-static int ns_call_snv_host(ns_ctx *ctx, const ns_params *prm, int n, int64_t P, const uint8_t *ref, const int32_t *counts,
-                            const uint16_t *counts16, ns_out *out)
+static int ns_snv_device_body(ns_ctx *ctx, const ns_params *prm, int n, int64_t P, const uint8_t *d_ref,
+                              const int32_t *d_counts, ns_out *out)
 {
-    if (!ctx)
-        return NS_ERR_ARG;
-    if (!prm || !out || n < 1 || P < 0 || (P > 0 && (!ref || (!counts && !counts16)))) {
-        ctx->err = "ns_call_snv: bad argument";
-        return NS_ERR_ARG;
-    }
     CK(cudaSetDevice(ctx->device));
     ns_reset_out(ctx, out);
     ns_params dprm;
@@ -837,15 +1182,56 @@ static int ns_call_snv_host(ns_ctx *ctx, const ns_params *prm, int n, int64_t P,
     int rc = ns_prepare_params(ctx, prm, n, &dprm, &qtab);
     if (rc)
         return rc;
+    if ((rc = ns_pool_begin(ctx, n)))
+        return rc;
     cudaEvent_t t0 = ctx->ev[8], t1 = ctx->ev[9];
     CK(cudaEventRecord(t0, ctx->stream));
     const int64_t U = 3 * P;
     const int64_t chunk = U > 0 ? ns_pick_chunk(ctx, n, U) : 0;
-    const int64_t pchunk = chunk / 3;
+    int64_t emit_off = 0;
+    RowSink sink = ns_sink_from_out(out);
+    ns_unit_src src;
+    memset(&src, 0, sizeof(src));
+    src.mode = 0;
+    src.n = n;
+    src.counts = d_counts;
+    src.ref = d_ref;
+    for (int64_t u0 = 0; u0 < U; u0 += chunk) {
+        int Uc = (int)((U - u0 < chunk) ? (U - u0) : chunk);
+        rc = ns_run_chunk(ctx, dprm, qtab, src, u0, u0, Uc, out, &sink, &emit_off);
+        if (rc)
+            return rc;
+    }
+    if ((rc = ns_pool_finish(ctx, dprm, qtab, n, 0, out, &sink, &emit_off, U)))
+        return rc;
+    CK(cudaEventRecord(t1, ctx->stream));
+    CK(cudaEventSynchronize(t1));
+    ctx->tm.total_ms = ev_ms(t0, t1);
+    ns_finish_out(ctx, out, U, emit_off);
+    return ns_check_overflow(ctx, out, emit_off);
+}
+
+/* SNV planes on the host.  Chunks of positions are pulled from `q` (one context: its own queue, every chunk; a
+ * multi-GPU call: one queue shared by the host threads of all devices); H2D of the next chunk runs on
+ * the copy stream under the kernels of the current one (two staging buffers). */
+int ns_snv_host_queue(ns_ctx *ctx, const ns_params *prm, int n, int64_t P, const uint8_t *ref, const int32_t *counts,
+                      const uint16_t *counts16, ns_out *out, RowSink *sink, ChunkQueue *q, int slot, int64_t *emitted)
+{
+    CK(cudaSetDevice(ctx->device));
+    ns_params dprm;
+    const double *qtab = nullptr;
+    int rc = ns_prepare_params(ctx, prm, n, &dprm, &qtab);
+    if (rc)
+        return rc;
+    if ((rc = ns_pool_begin(ctx, n)))
+        return rc;
+    cudaEvent_t t0 = ctx->ev[8], t1 = ctx->ev[9];
+    CK(cudaEventRecord(t0, ctx->stream));
+    const int64_t pchunk = q->pchunk;
     int64_t emit_off = 0;
     const size_t row_elems = (size_t)9 * n;
-    /* double-buffered staging: the copy stream runs one chunk ahead of the compute stream */
-    auto stage = [&](int64_t p0, int buf) -> int {
+    auto stage = [&](int64_t ci, int buf) -> int {
+        const int64_t p0 = ci * pchunk;
         int64_t pc = (P - p0 < pchunk) ? (P - p0) : pchunk;
         cudaError_t e;
         if ((e = ctx->in_counts[buf].reserve((size_t)pc * row_elems)) || (e = ctx->in_ref[buf].reserve((size_t)pc))) {
@@ -871,23 +1257,30 @@ static int ns_call_snv_host(ns_ctx *ctx, const ns_params *prm, int n, int64_t P,
         CK(cudaEventRecord(ctx->ev_h2d[buf], ctx->copy_stream));
         return NS_OK;
     };
+    auto take = [&]() -> int64_t {
+        if (q->failed.load())
+            return -1;
+        const int64_t ci = q->next.fetch_add(1);
+        if (ci >= q->n_chunks)
+            return -1;
+        if (!q->owner.empty())
+            q->owner[(size_t)ci] = slot;
+        return ci;
+    };
     /* the staging buffers start out free */
     CK(cudaEventRecord(ctx->ev_free[0], ctx->stream));
     CK(cudaEventRecord(ctx->ev_free[1], ctx->stream));
-    if (P > 0) {
-        rc = stage(0, 0);
-        if (rc)
+    int64_t cur = take();
+    if (cur >= 0 && (rc = stage(cur, 0)))
+        return rc;
+    int64_t k = 0;
+    while (cur >= 0) {
+        const int buf = (int)(k & 1);
+        const int64_t nxt = take();
+        if (nxt >= 0 && (rc = stage(nxt, buf ^ 1)))
             return rc;
-    }
-    int64_t ci = 0;
-    for (int64_t p0 = 0; p0 < P; p0 += pchunk, ci++) {
-        const int buf = (int)(ci & 1);
+        const int64_t p0 = cur * pchunk;
         const int64_t pc = (P - p0 < pchunk) ? (P - p0) : pchunk;
-        if (p0 + pchunk < P) {
-            rc = stage(p0 + pchunk, buf ^ 1);
-            if (rc)
-                return rc;
-        }
         CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_h2d[buf], 0));
         ns_unit_src src;
         memset(&src, 0, sizeof(src));
@@ -895,44 +1288,51 @@ static int ns_call_snv_host(ns_ctx *ctx, const ns_params *prm, int n, int64_t P,
         src.n = n;
         src.counts = ctx->in_counts[buf].p;
         src.ref = ctx->in_ref[buf].p;
-        rc = ns_run_chunk(ctx, dprm, qtab, src, 0, 3 * p0, (int)(3 * pc), out, &emit_off);
+        rc = ns_run_chunk(ctx, dprm, qtab, src, 0, 3 * p0, (int)(3 * pc), out, sink, &emit_off);
         if (rc)
             return rc;
         CK(cudaEventRecord(ctx->ev_free[buf], ctx->stream));
+        cur = nxt;
+        k++;
     }
+    if ((rc = ns_pool_finish(ctx, dprm, qtab, n, 0, out, sink, &emit_off, 3 * P)))
+        return rc;
     CK(cudaEventRecord(t1, ctx->stream));
     CK(cudaEventSynchronize(t1));
     ctx->tm.total_ms = ev_ms(t0, t1);
-    ns_finish_out(out, U, emit_off);
-    if (emit_off > out->emit_cap && (out->pvalue || out->gq || out->emit_unit)) {
-        ctx->err = "more emitted units than out->emit_cap";
-        return NS_ERR_EMIT_OVERFLOW;
-    }
+    *emitted = emit_off;
     return NS_OK;
 }
 
-int ns_call_snv(ns_ctx *ctx, const ns_params *prm, int n, int64_t P, const uint8_t *ref, const int32_t *counts,
-                ns_out *out)
-{
-    return ns_call_snv_host(ctx, prm, n, P, ref, counts, nullptr, out);
-}
-
-int ns_call_snv_u16(ns_ctx *ctx, const ns_params *prm, int n, int64_t P, const uint8_t *ref, const uint16_t *counts,
-                    ns_out *out)
-{
-    return ns_call_snv_host(ctx, prm, n, P, ref, nullptr, counts, out);
-}
-
-int ns_call_units(ns_ctx *ctx, const ns_params *prm, int n, int64_t U, const int32_t *dp, const int32_t *vp,
-                  const int32_t *vm, const int32_t *rp, const int32_t *rm, const uint8_t *is_indel, int plain,
-                  ns_out *out)
+static int ns_call_snv_host(ns_ctx *ctx, const ns_params *prm, int n, int64_t P, const uint8_t *ref, const int32_t *counts,
+                            const uint16_t *counts16, ns_out *out)
 {
     if (!ctx)
         return NS_ERR_ARG;
-    if (!prm || !out || n < 1 || U < 0 || (U > 0 && (!dp || !vp))) {
-        ctx->err = "ns_call_units: bad argument";
+    if (!prm || !out || n < 1 || P < 0 || (P > 0 && (!ref || (!counts && !counts16)))) {
+        ctx->err = "ns_call_snv: bad argument";
         return NS_ERR_ARG;
     }
+    ns_reset_out(ctx, out);
+    const int64_t U = 3 * P;
+    ChunkQueue q;
+    q.pchunk = U > 0 ? ns_pick_chunk(ctx, n, U) / 3 : 1;
+    q.n_chunks = P > 0 ? (P + q.pchunk - 1) / q.pchunk : 0;
+    RowSink sink = ns_sink_from_out(out);
+    int64_t emitted = 0;
+    int rc = ns_snv_host_queue(ctx, prm, n, P, ref, counts, counts16, out, &sink, &q, 0, &emitted);
+    if (rc) {
+        ns_drain(ctx);
+        return rc;
+    }
+    ns_finish_out(ctx, out, U, emitted);
+    return ns_check_overflow(ctx, out, emitted);
+}
+
+static int ns_call_units_body(ns_ctx *ctx, const ns_params *prm, int n, int64_t U, const int32_t *dp, const int32_t *vp,
+                              const int32_t *vm, const int32_t *rp, const int32_t *rm, const uint8_t *is_indel, int plain,
+                              ns_out *out)
+{
     CK(cudaSetDevice(ctx->device));
     ns_reset_out(ctx, out);
     ns_params dprm;
@@ -940,10 +1340,13 @@ int ns_call_units(ns_ctx *ctx, const ns_params *prm, int n, int64_t U, const int
     int rc = ns_prepare_params(ctx, prm, n, &dprm, &qtab);
     if (rc)
         return rc;
+    if ((rc = ns_pool_begin(ctx, n)))
+        return rc;
     cudaEvent_t t0 = ctx->ev[8], t1 = ctx->ev[9];
     CK(cudaEventRecord(t0, ctx->stream));
     const int64_t chunk = U > 0 ? ns_pick_chunk(ctx, n, U) : 0;
     int64_t emit_off = 0;
+    RowSink sink = ns_sink_from_out(out);
     const int32_t *hrows[5] = {dp, vp, vm, rp, rm};
     for (int64_t u0 = 0; u0 < U; u0 += chunk) {
         const int Uc = (int)((U - u0 < chunk) ? (U - u0) : chunk);
@@ -979,19 +1382,62 @@ int ns_call_units(ns_ctx *ctx, const ns_params *prm, int n, int64_t U, const int
         src.vm = drows[2];
         src.rp = drows[3];
         src.rm = drows[4];
-        rc = ns_run_chunk(ctx, dprm, qtab, src, 0, u0, Uc, out, &emit_off);
+        rc = ns_run_chunk(ctx, dprm, qtab, src, 0, u0, Uc, out, &sink, &emit_off);
         if (rc)
             return rc;
     }
+    if ((rc = ns_pool_finish(ctx, dprm, qtab, n, plain, out, &sink, &emit_off, U)))
+        return rc;
     CK(cudaEventRecord(t1, ctx->stream));
     CK(cudaEventSynchronize(t1));
     ctx->tm.total_ms = ev_ms(t0, t1);
-    ns_finish_out(out, U, emit_off);
-    if (emit_off > out->emit_cap && (out->pvalue || out->gq || out->emit_unit)) {
-        ctx->err = "more emitted units than out->emit_cap";
-        return NS_ERR_EMIT_OVERFLOW;
+    ns_finish_out(ctx, out, U, emit_off);
+    return ns_check_overflow(ctx, out, emit_off);
+}
+
+extern "C" {
+
+int ns_call_snv_device(ns_ctx *ctx, const ns_params *prm, int n, int64_t P, const uint8_t *d_ref,
+                       const int32_t *d_counts, ns_out *out)
+{
+    if (!ctx)
+        return NS_ERR_ARG;
+    if (!prm || !out || n < 1 || P < 0 || (P > 0 && (!d_ref || !d_counts))) {
+        ctx->err = "ns_call_snv_device: bad argument";
+        return NS_ERR_ARG;
     }
-    return NS_OK;
+    int rc = ns_snv_device_body(ctx, prm, n, P, d_ref, d_counts, out);
+    if (rc && rc != NS_ERR_EMIT_OVERFLOW)
+        ns_drain(ctx);
+    return rc;
+}
+
+int ns_call_snv(ns_ctx *ctx, const ns_params *prm, int n, int64_t P, const uint8_t *ref, const int32_t *counts,
+                ns_out *out)
+{
+    return ns_call_snv_host(ctx, prm, n, P, ref, counts, nullptr, out);
+}
+
+int ns_call_snv_u16(ns_ctx *ctx, const ns_params *prm, int n, int64_t P, const uint8_t *ref, const uint16_t *counts,
+                    ns_out *out)
+{
+    return ns_call_snv_host(ctx, prm, n, P, ref, nullptr, counts, out);
+}
+
+int ns_call_units(ns_ctx *ctx, const ns_params *prm, int n, int64_t U, const int32_t *dp, const int32_t *vp,
+                  const int32_t *vm, const int32_t *rp, const int32_t *rm, const uint8_t *is_indel, int plain,
+                  ns_out *out)
+{
+    if (!ctx)
+        return NS_ERR_ARG;
+    if (!prm || !out || n < 1 || U < 0 || (U > 0 && (!dp || !vp))) {
+        ctx->err = "ns_call_units: bad argument";
+        return NS_ERR_ARG;
+    }
+    int rc = ns_call_units_body(ctx, prm, n, U, dp, vp, vm, rp, rm, is_indel, plain, out);
+    if (rc && rc != NS_ERR_EMIT_OVERFLOW)
+        ns_drain(ctx);
+    return rc;
 }
 
 int ns_glmrob_nb(ns_ctx *ctx, const ns_params *prm, int n, const int32_t *y, const int32_t *x, double *sigma,

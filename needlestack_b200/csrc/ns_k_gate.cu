@@ -528,13 +528,26 @@ __global__ void k_scan_total(const int *flag, const int *excl, int n, int *total
         *total = n > 0 ? excl[n - 1] + flag[n - 1] : 0;
 }
 
-/* rows of emitted units, in unit order, into the packed planes */
+/* rows of emitted units, in unit order, into the packed planes; units whose fit runs in the call-wide pool only
+ * record how many emitted rows precede them (their insertion point at the end of the call); counts the skipped
+ * positions' units on the way */
 __global__ void k_pack(int n, int n_units, int64_t u0, int64_t emit_off, int cap, ns_unit_arrays ua,
-                       ns_planes src, ns_planes dst, int64_t *emit_unit, int *emit_index_out)
+                       ns_planes src, ns_planes dst, int64_t *emit_unit, int *emit_index_out, int64_t *pool_lightpos,
+                       ns_counters *cnt)
 {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int wpb = blockDim.x >> 5;
+    int n_skip = 0;
     for (int u = blockIdx.x * wpb + warp; u < n_units; u += gridDim.x * wpb) {
+        const uint32_t fl = ua.flags[u];
+        n_skip += (fl & NS_F_SKIPPED) != 0;
+        if (fl & NS_F_POOLED) {
+            if (lane == 0) {
+                pool_lightpos[ua.row[u]] = emit_off + ua.emitidx[u];
+                emit_index_out[u] = -1;
+            }
+            continue;
+        }
         if (!ua.emitflag[u]) {
             if (lane == 0)
                 emit_index_out[u] = -1;
@@ -561,6 +574,47 @@ __global__ void k_pack(int n, int n_units, int64_t u0, int64_t emit_off, int cap
             dst.pooled[(size_t)d * 8 + lane] = src.pooled[(size_t)ua.row[u] * 8 + lane];
         if (lane == 0)
             emit_unit[d] = u0 + u;
+    }
+    if (lane == 0 && n_skip)
+        atomicAdd(&cnt->n_skipped, n_skip);
+}
+
+/* Copies the count rows of `count` listed units of the current chunk into the pool slots base .. base+count-1
+ * (warp per unit), marks the units NS_F_POOLED in the chunk's arrays (ua.row[u] then holds the pool slot) and
+ * initialises the counter block of the cluster-kernel launch that will fit them. */
+__global__ void k_pool_gather(ns_unit_src src, int64_t u0_src, int64_t u_off, const int *list, int count,
+                              ns_unit_arrays ua, ns_pool_dev pool, int base, ns_counters *launch_cnt)
+{
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int wpb = blockDim.x >> 5;
+    const int n = src.n;
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        ns_counters z;
+        memset(&z, 0, sizeof(z));
+        z.n_pre = count;
+        *launch_cnt = z;
+    }
+    for (int i = blockIdx.x * wpb + warp; i < count; i += gridDim.x * wpb) {
+        const int u = list[i];
+        const int slot = base + i;
+        const ns_rows r = ns_unit_rows(src, u0_src + u);
+        const size_t o = (size_t)slot * n;
+        for (int k = lane; k < n; k += 32) {
+            pool.dp[o + k] = r.dp[k];
+            pool.vp[o + k] = r.vp[k];
+            pool.vm[o + k] = r.vm ? r.vm[k] : 0;
+            pool.rp[o + k] = r.rp ? r.rp[k] : 0;
+            pool.rm[o + k] = r.rm ? r.rm[k] : 0;
+        }
+        if (lane == 0) {
+            const uint32_t fl = ua.flags[u];
+            pool.flags[slot] = fl;
+            pool.is_indel[slot] = (uint8_t)r.is_indel;
+            pool.unit[slot] = u_off + u;
+            pool.lightpos[slot] = 0;
+            ua.flags[u] = fl | NS_F_POOLED;
+            ua.row[u] = slot;
+        }
     }
 }
 

@@ -23,6 +23,8 @@ k_post(ns_unit_src src, ns_params prm, int64_t u0, ns_unit_arrays ua, ns_planes 
         if (idx >= n_post)
             break;
         const int u = ua.post_list[idx];
+        if (ua.flags[u] & NS_F_POOLED)
+            continue; /* fitted in the call-wide pool: its rows are computed at the end of the call */
         const size_t row = (size_t)ua.row[u];
         ns_rows r = ns_unit_rows(src, u0 + u);
         ns_unit_out o;

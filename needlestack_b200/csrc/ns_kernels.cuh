@@ -19,11 +19,15 @@
 #define NS_WPB_GATE 8
 #define NS_QTAB_LEN 65536
 
+/* internal unit flag (never leaves the library): the unit's fit runs in the call-wide pool of cluster-path units;
+ * the chunk it came from skips it in k_post / k_pack and the pool delivers its results at the end of the call */
+#define NS_F_POOLED 0x80000000u
+
 /* ---- device-side bookkeeping ------------------------------------------------------- */
 struct ns_counters {
     int n_fit, n_post, n_rows, n_emit;
     int next_fit, next_post, n_heavy, next_heavy;
-    int n_pre, next_pre, n_light, pad1; /* n_pre: units predicted heavy by the gate kernel; n_light: the rest */
+    int n_pre, next_pre, n_light, n_skipped; /* n_pre: units predicted heavy by the gate kernel; n_light: the rest */
     unsigned long long n_seed, n_lattice, n_quad, pad2;
     unsigned long long fast_seed, fast_lattice;
 };
@@ -31,6 +35,15 @@ struct ns_counters {
 struct ns_planes {
     double *pvalue, *qvalue, *gq, *qval_minaf, *sor, *rvsb, *fs, *pooled;
     uint8_t *gt, *status;
+};
+
+/* device side of the call-wide pool: the five count rows of every pooled unit (copied out of the chunk's input
+ * buffers, which are recycled), its flag word, global unit id and the number of emitted rows that precede it */
+struct ns_pool_dev {
+    int32_t *dp, *vp, *vm, *rp, *rm; /* [cap][n] */
+    uint8_t *is_indel;               /* [cap] */
+    uint32_t *flags;                 /* [cap] */
+    int64_t *unit, *lightpos;        /* [cap] */
 };
 
 struct ns_unit_arrays {
@@ -52,7 +65,10 @@ __global__ void k_post(ns_unit_src src, ns_params prm, int64_t u0, ns_unit_array
                        const double *qtab, int qtab_len, ns_counters *cnt);
 __global__ void k_scan_total(const int *flag, const int *excl, int n, int *total);
 __global__ void k_pack(int n, int n_units, int64_t u0, int64_t emit_off, int cap, ns_unit_arrays ua,
-                       ns_planes src, ns_planes dst, int64_t *emit_unit, int *emit_index_out);
+                       ns_planes src, ns_planes dst, int64_t *emit_unit, int *emit_index_out, int64_t *pool_lightpos,
+                       ns_counters *cnt);
+__global__ void k_pool_gather(ns_unit_src src, int64_t u0_src, int64_t u_off, const int *list, int count,
+                              ns_unit_arrays ua, ns_pool_dev pool, int base, ns_counters *launch_cnt);
 __global__ void k_qtab(double *tabN, double *tabT, int len, double sigma_normal, double afmin);
 __global__ void k_qgrid(int n, const int32_t *cov, const int32_t *ma, double sigma, double slope, int64_t m, const int32_t *gx,
                         const int32_t *gy, double *out);

@@ -41,8 +41,11 @@ CONFIGS = {
 }
 
 
-def generate(cfg: Config, P=None, seed=None, p_variant=1e-3, p_germline=1e-4):
-    """Returns (ref uint8 [P], counts int32 [P][9][n]).  Chunk-wise callers pass P and a seed."""
+def generate(cfg: Config, P=None, seed=None, p_variant=1e-3, p_germline=1e-4, p_refswap=0.0):
+    """Returns (ref uint8 [P], counts int32 [P][9][n]).  Chunk-wise callers pass P and a seed.
+    p_refswap: probability that a position has the reference genome carrying the MINOR allele (the planes of the
+    REF base and of one ALT base are exchanged, so that ALT/DP > 0.8 in most samples): the reference-inversion
+    branch of needlestack.r:330-337.  Drawn after everything else: 0 leaves the batches of earlier seeds unchanged."""
     P = cfg.P if P is None else int(P)
     n = cfg.n
     rng = np.random.Generator(np.random.PCG64(cfg.seed if seed is None else seed))
@@ -106,6 +109,12 @@ def generate(cfg: Config, P=None, seed=None, p_variant=1e-3, p_germline=1e-4):
         counts[pidx, 5 + b, :] = rev[:, k, :]
     counts[pidx, 1 + ref, :] = rfwd
     counts[pidx, 5 + ref, :] = rrev
+    if p_refswap > 0:
+        for p in np.where(rng.random(P) < p_refswap)[0]:
+            b = alts[ref[p], rng.integers(0, 3)]
+            r = ref[p]
+            counts[p, [1 + r, 1 + b]] = counts[p, [1 + b, 1 + r]]
+            counts[p, [5 + r, 5 + b]] = counts[p, [5 + b, 5 + r]]
     return ref, counts
 
 
