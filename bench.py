@@ -48,6 +48,9 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--p-germline", type=float, default=1e-4)
     ap.add_argument("--dump-cycles", default="")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: every rank its own region (torchrun, one process per GPU); strong: ONE workload over "
+                         "--gpus devices from ONE host process (ns_multi_call_snv), run without torchrun")
     return ap.parse_args()
 
 
@@ -232,6 +235,87 @@ def parity_check(caller, ns, ref_np, counts_np, O, Ps):
     return out
 
 
+def strong_main(a, cfg, P, n, config, torch, ns):
+    """ONE workload (P positions) over a.gpus devices from this one host process: the planes live in page-locked host
+    memory, ns_multi_call_snv hands chunks of positions to one host thread per device and gathers the rows in
+    genomic order.  Every step is a whole call (H2D, kernels, D2H, gather inside the timed region)."""
+    nd = torch.cuda.device_count()
+    if a.gpus > nd:
+        raise SystemExit(f"bench.py --scaling strong --gpus {a.gpus}: only {nd} devices visible")
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(0)
+    h_counts = ns.PinnedArray((P, 9, n), np.int32)
+    h_ref = ns.PinnedArray((P,), np.uint8)
+    # the batch is generated on device 0 in slices (a 10 Mb x 400 sample batch does not fit next to torch's temporaries)
+    slice_p = max(1, min(P, int(2.0e9 // (36 * n))))
+    Ph = min(P, REF_SAMPLE_POSITIONS)
+    for k, p0 in enumerate(range(0, P, slice_p)):
+        pc = min(slice_p, P - p0)
+        d_ref, d_counts = generate_torch(cfg, pc, cfg.seed + 7919 * k, dev, a.p_germline)
+        torch.from_numpy(h_counts.array[p0:p0 + pc]).copy_(d_counts)
+        torch.from_numpy(h_ref.array[p0:p0 + pc]).copy_(d_ref)
+        del d_ref, d_counts
+    from needlestack_b200 import synth
+    h_ref.array[:Ph], h_counts.array[:Ph] = synth.generate(cfg, P=Ph, seed=cfg.seed, p_germline=a.p_germline)
+    torch.cuda.synchronize()
+    torch.cuda.empty_cache()
+    prm = ns.make_params()
+    m = ns.MultiCaller(list(range(a.gpus)), reuse_outputs=True)
+    for _ in range(max(a.warmup, 1)):
+        R = m.call_snv(h_ref.array, h_counts.array, prm=prm)
+    samplers = [ClockSampler(i) for i in range(a.gpus)]
+    for sp in samplers:
+        sp.start()
+    fitted = 0
+    per_dev = [dict(chunks=0, wall_ms=0.0, device_ms=0.0, gate_ms=0.0, fit_ms=0.0, pool_tail_ms=0.0) for _ in range(a.gpus)]
+    launches = 0
+    t0 = time.perf_counter()
+    for _ in range(a.steps):
+        R = m.call_snv(h_ref.array, h_counts.array, prm=prm)
+        fitted += R.n_fitted
+        for d, t in zip(per_dev, m.timings()):
+            d["chunks"] += t["chunks"]
+            d["wall_ms"] += t["wall_ms"]
+            d["device_ms"] += t["total_ms"]
+            d["gate_ms"] += t["gate_ms"]
+            d["fit_ms"] += t["fit_ms"]
+            d["pool_tail_ms"] += t["pool_tail_ms"]
+            launches += t["kernel_launches"]
+    ms = (time.perf_counter() - t0) * 1e3
+    clocks = [sp.stop() for sp in samplers]
+    for d in per_dev:
+        for k in d:
+            d[k] = d[k] / a.steps
+    U = 3 * P
+    d2h = U * (8 + 8 + 8 + 4 + 4 + 4) + R.n_emitted * (n * 58 + 8 * 8 + 8)
+    value = fitted / (ms * 1e-3)
+    # single-context result of the same call: the gather must not change anything
+    with ns.Caller(0) as c1:
+        R1 = c1.call_snv(h_ref.array, h_counts.array, prm=prm)
+    same = bool(R1.n_emitted == R.n_emitted and R1.n_fitted == R.n_fitted and np.array_equal(R1.emit_unit, R.emit_unit)
+                and np.array_equal(R1.gq, R.gq, equal_nan=True) and np.array_equal(R1.sigma, R.sigma, equal_nan=True))
+    config = dict(config, parallelism=f"one host process, {a.gpus} devices, queue of position chunks (ns_multi_call_snv)",
+                  positions_total=P)
+    config.pop("positions_per_gpu", None)
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
+            "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic", "config": config,
+            "clocks": {"sm_mhz": min((c["sm_mhz"] or 0) for c in clocks), "sm_max_mhz": max((c["sm_max_mhz"] or 0) for c in clocks),
+                       "reasons": sorted(set(r for c in clocks for r in c["reasons"]))},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": int(h_counts.nbytes + h_ref.nbytes),
+                    "d2h_bytes_per_step": int(d2h), "ms_per_step": ms / a.steps,
+                    "api": "needlestack_b200.MultiCaller.call_snv -> ns_multi_call_snv (C ABI), host planes in, host results out"},
+            "value_note": "one workload from host memory: `value` is the end-to-end rate (there is no device-resident form of a "
+                          "multi-device call); timed by the host clock around the synchronous calls",
+            "gpu_launches": int(launches), "per_device": per_dev,
+            "detail": {"fitted_per_step": R.n_fitted, "emitted_per_step": R.n_emitted,
+                       "identical_to_single_device_call": same,
+                       "site_alleles_processed_per_s": U * a.steps / (ms * 1e-3)}}
+    print(json.dumps(line))
+    m.close()
+    return 0
+
+
 def main():
     a = parse()
     from needlestack_b200 import synth
@@ -284,13 +368,16 @@ def main():
     import needlestack_b200 as ns
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the B200 path has no CPU fallback")
+    if a.scaling == "strong":
+        if rank != 0:
+            return 0
+        return strong_main(a, cfg, P, n, config, torch, ns)
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     dist = None
     if world > 1:
-        # keep stdout to the one JSON line: at any NCCL_DEBUG level NCCL prints its version banner there
-        if not os.environ.get("NS_KEEP_NCCL_DEBUG"):
-            os.environ.pop("NCCL_DEBUG", None)
+        # stdout carries the one JSON line: NCCL's log (version banner, rank/ring lines at NCCL_DEBUG=INFO) goes to stderr
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
 
@@ -313,6 +400,14 @@ def main():
         t = torch.tensor([x], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
         return float(t.item())
+
+    def allgather(x):
+        if dist is None:
+            return [x]
+        t = torch.tensor([x], device=dev, dtype=torch.float64)
+        out = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(out, t)
+        return [float(o.item()) for o in out]
 
     d_ref, d_counts = generate_torch(cfg, P, cfg.seed + 1000 * rank, dev, a.p_germline)
     # the first positions of every rank's batch come from the numpy generator: for rank 0 they are exactly the sample the
@@ -360,6 +455,7 @@ def main():
                             slope=R.slope)
     clocks = sampler.stop()
     ms_max = allmax(ms)
+    per_rank_ms = allgather(ms / a.steps)
     fitted_all = allsum(fitted)
     launches = int(tm_sum.get("kernel_launches", 0))
     value = fitted_all / (ms_max * 1e-3)
@@ -428,12 +524,15 @@ def main():
             fitted_h += Rh.n_fitted
         e1.record()
         barrier()
-        ms_h = allmax(e0.elapsed_time(e1))
+        ms_h_own = e0.elapsed_time(e1)
+        ms_h = allmax(ms_h_own)
+        per_rank_ms_e2e = allgather(ms_h_own / a.steps)
         U = 3 * P
         d2h = U * (8 + 8 + 8 + 4 + 4 + 4) + Rh.n_emitted * (n * 58 + 8 * 8 + 8)
         e2e = {"value": allsum(fitted_h) / (ms_h * 1e-3), "unit": UNIT,
                "h2d_bytes_per_step": int(h_counts.nbytes + h_ref.nbytes), "d2h_bytes_per_step": int(d2h),
-               "ms_per_step": ms_h / a.steps, "api": "needlestack_b200.Caller.call_snv -> ns_call_snv (C ABI)"}
+               "ms_per_step": ms_h / a.steps, "per_rank_ms": per_rank_ms_e2e,
+               "api": "needlestack_b200.Caller.call_snv -> ns_call_snv (C ABI)"}
         assert Rh.n_fitted == R.n_fitted and Rh.n_emitted == R.n_emitted
         ref_np = h_ref.array[: min(P, REF_SAMPLE_POSITIONS)].copy()
         counts_np = h_counts.array[: min(P, REF_SAMPLE_POSITIONS)].copy()
@@ -476,7 +575,11 @@ def main():
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config, "clocks": clocks,
                 "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "roofline_gate": roofline_gate,
                 "cpu_baseline": cpu, "parity_check": parity_rep,
+                "per_rank_ms": per_rank_ms,
                 "detail": {"site_alleles_processed_per_s": units_all / (ms_max * 1e-3),
+                           "pool": {"units_per_step_rank0": tm_sum.get("pool_units", 0) / a.steps,
+                                    "tail_ms_per_step_rank0": tm_sum.get("pool_tail_ms", 0) / a.steps,
+                                    "chunks_per_step_rank0": tm_sum.get("chunks", 0) / a.steps},
                            "gate_pass_fraction": fitted_all / units_all, "fitted_per_step_rank0": R.n_fitted,
                            "emitted_per_step_rank0": n_emitted,
                            "heavy_units_per_step_rank0": tm_sum.get("n_heavy", 0) / a.steps,

@@ -224,6 +224,26 @@ const char *ns_table_indel_seq(const ns_table *t, int64_t u);
 const int32_t *ns_table_indel_vp(const ns_table *t);   /* [Ui][n] forward-strand counts */
 const int32_t *ns_table_indel_vm(const ns_table *t);   /* [Ui][n] reverse-strand counts */
 
+/* ---- one workload over several GPUs from one host process -------------------------------------
+ * Replaces the reference's region split + final merge: `--nsplit` / bin/bed_cut.r:19-58 cut the BED into pieces, one
+ * single-threaded Rscript per piece (needlestack.nf:421-503), per-piece VCFs concatenated and sorted at the end
+ * (needlestack.nf:546-553).  Here ONE call takes the whole table: a queue of position chunks, one host thread per
+ * device pulling from it, results gathered in chunk (= genomic) order on the host; outputs are exactly those of
+ * ns_call_snv on one device.  devices: CUDA ordinals (an ordinal may be listed twice: two contexts on one GPU).
+ * This is how a single-threaded R process reaches every GPU of the box with one .Call. */
+typedef struct ns_multi ns_multi;
+ns_multi *ns_create_multi(const int *devices, int n_devices, char *err, size_t errlen);
+void ns_destroy_multi(ns_multi *m);
+int ns_multi_devices(const ns_multi *m);
+const char *ns_multi_last_error(ns_multi *m);
+int ns_multi_call_snv(ns_multi *m, const ns_params *prm, int n_samples, int64_t n_positions, const uint8_t *ref,
+                      const int32_t *counts, ns_out *out);
+int ns_multi_call_snv_u16(ns_multi *m, const ns_params *prm, int n_samples, int64_t n_positions, const uint8_t *ref,
+                          const uint16_t *counts, ns_out *out);
+/* device timings of slot `slot` in the last multi call (t->chunks = chunks it pulled) and the wall time of its host
+ * thread, ms */
+int ns_multi_get_timings(ns_multi *m, int slot, ns_timings *t, double *wall_ms);
+
 /* FP64 FMA peak of the context's device, TFLOP/s (the denominator of the fit roofline) */
 int ns_measure_fp64_peak(ns_ctx *ctx, double *tflops);
 

@@ -58,6 +58,15 @@ def load_library():
     L.ns_qvalue_grid.argtypes = [vp, C.c_double, C.c_double, C.c_int, vp, vp, C.c_int64, vp, vp, c_dp]
     L.ns_glmrob_nb.argtypes = [vp, C.POINTER(NsParams), C.c_int, vp, vp, c_dp, c_dp, c_dp, c_dp, c_dp, c_ip, c_up]
     L.ns_measure_fp64_peak.argtypes = [vp, c_dp]
+    L.ns_create_multi.restype = vp
+    L.ns_create_multi.argtypes = [c_ip, C.c_int, C.c_char_p, C.c_size_t]
+    L.ns_destroy_multi.argtypes = [vp]
+    L.ns_multi_devices.argtypes = [vp]
+    L.ns_multi_last_error.restype = C.c_char_p
+    L.ns_multi_last_error.argtypes = [vp]
+    L.ns_multi_call_snv.argtypes = [vp, C.POINTER(NsParams), C.c_int, C.c_int64, vp, vp, C.POINTER(NsOut)]
+    L.ns_multi_call_snv_u16.argtypes = [vp, C.POINTER(NsParams), C.c_int, C.c_int64, vp, vp, C.POINTER(NsOut)]
+    L.ns_multi_get_timings.argtypes = [vp, C.c_int, C.POINTER(NsTimings), c_dp]
     L.ns_table_parse.restype = vp
     L.ns_table_parse.argtypes = [C.c_char_p, C.c_size_t, C.c_int, C.c_int, C.c_int, C.c_char_p, C.c_size_t]
     L.ns_table_free.argtypes = [vp]
@@ -85,6 +94,8 @@ def load_library():
 EXPORTED_SYMBOLS = ("ns_abi_version", "ns_sizeof", "ns_params_glm_default", "ns_params_caller_default", "ns_create", "ns_destroy",
                     "ns_last_error", "ns_set_stream", "ns_alloc_pinned", "ns_free_pinned", "ns_get_timings",
                     "ns_call_snv", "ns_call_snv_u16", "ns_call_snv_device", "ns_call_units", "ns_glmrob_nb", "ns_qvalue_grid", "ns_measure_fp64_peak",
+                    "ns_create_multi", "ns_destroy_multi", "ns_multi_devices", "ns_multi_last_error", "ns_multi_call_snv",
+                    "ns_multi_call_snv_u16", "ns_multi_get_timings",
                     "ns_table_parse", "ns_table_free", "ns_table_positions", "ns_table_samples",
                     "ns_table_counts_pinned", "ns_table_counts", "ns_table_ref", "ns_table_ref_text", "ns_table_loc",
                     "ns_table_chrom", "ns_table_n_chrom", "ns_table_chrom_name", "ns_table_indel_cov",
@@ -377,6 +388,66 @@ class Caller:
         return dict(coverage=np.asarray(x, dtype=float), ma_count=np.asarray(y, dtype=float),
                     coef=dict(sigma=sigma.value, slope=slope.value), pvalues=pv, qvalues=qv, GQ=gq,
                     extra_rob=bool(er.value), flags=fl.value)
+
+
+class MultiCaller(Caller):
+    """One workload over several GPUs from this ONE host process (ns_multi_*): a queue of position chunks, one host
+    thread per device inside the library, results gathered in genomic order - the role of the reference's --nsplit
+    region split and final merge (needlestack.nf:421-503, :546-553).  call_snv returns exactly what Caller.call_snv
+    returns on one device.  devices: CUDA ordinals (an ordinal listed twice = two contexts on that GPU)."""
+
+    def __init__(self, devices, reuse_outputs=False):
+        self._reuse = bool(reuse_outputs)
+        self._pool = {}
+        self._L = load_library()
+        self._ctx = None
+        self.devices = [int(d) for d in devices]
+        err = C.create_string_buffer(512)
+        arr = (C.c_int32 * len(self.devices))(*self.devices)
+        self._m = self._L.ns_create_multi(arr, len(self.devices), err, 512)
+        if not self._m:
+            raise NeedlestackError(err.value.decode() or "ns_create_multi failed")
+
+    def close(self):
+        if getattr(self, "_m", None):
+            self._L.ns_destroy_multi(self._m)
+            self._m = None
+        for pa in getattr(self, "_pool", {}).values():
+            pa.free()
+        self._pool = {}
+
+    def _check(self, rc):
+        if rc != 0:
+            raise NeedlestackError(f"ns error {rc}: {self._L.ns_multi_last_error(self._m).decode()}")
+
+    def call_snv(self, ref, counts, prm=None, emit_cap=None, want_rows=True, **kw):
+        prm = prm or make_params(**kw)
+        u16 = getattr(counts, "dtype", None) == np.uint16
+        counts = np.ascontiguousarray(counts, dtype=np.uint16 if u16 else np.int32)
+        ref = np.ascontiguousarray(ref, dtype=np.uint8)
+        P, nine, n = counts.shape
+        if nine != 9 or len(ref) != P:
+            raise ValueError("counts must be [P][9][n] and ref [P]")
+        fn = self._L.ns_multi_call_snv_u16 if u16 else self._L.ns_multi_call_snv
+        return self._run(lambda o: fn(self._m, C.byref(prm), n, P, _ptr(ref), _ptr(counts), C.byref(o)),
+                         prm, 3 * P, n, emit_cap, want_rows)
+
+    def timings(self):
+        """per device slot: the ns_timings of its context in the last call plus chunks pulled and host-thread wall ms"""
+        out = []
+        for s in range(len(self.devices)):
+            t, w = NsTimings(), C.c_double()
+            self._L.ns_multi_get_timings(self._m, s, C.byref(t), C.byref(w))
+            d = {k: getattr(t, k) for k, _ in NsTimings._fields_}
+            d["wall_ms"] = w.value
+            d["device"] = self.devices[s]
+            out.append(d)
+        return out
+
+    def _unsupported(self, *a, **k):
+        raise NeedlestackError("MultiCaller shards ns_call_snv only; use a Caller for this entry point")
+
+    call_snv_device = call_units = glmrob_nb = set_stream = fp64_peak_tflops = qvalue_grid = _unsupported
 
 
 def _qvalue_grid(self, sigma, slope, coverage, ma_count, gx, gy):
