@@ -117,6 +117,11 @@ typedef struct ns_out {
     /* batch counters (out) */
     int64_t n_fitted, n_gated, n_skipped;
     uint64_t n_seed, n_lattice, n_quad; /* work counters of SURVEY.md section 8(d) */
+    /* per emitted row (ABI 2; any may be NULL): sigma, slope, max(GQ) and the flag word of the row's unit.  A caller
+     * that only wants the variants leaves the per-unit arrays above NULL: a WGS-like chunk of 12 M units is 0.5 GB of
+     * per-unit device-to-host traffic against a few hundred emitted rows. */
+    double *row_sigma, *row_slope, *row_max_gq; /* [emit_cap] */
+    uint32_t *row_flags;                        /* [emit_cap] */
 } ns_out;
 
 /* per-call device timings of the last ns_call_* on this context, milliseconds */
@@ -223,6 +228,29 @@ const uint8_t *ns_table_indel_type(const ns_table *t); /* [Ui] 1 = deletion, 2 =
 const char *ns_table_indel_seq(const ns_table *t, int64_t u);
 const int32_t *ns_table_indel_vp(const ns_table *t);   /* [Ui][n] forward-strand counts */
 const int32_t *ns_table_indel_vm(const ns_table *t);   /* [Ui][n] reverse-strand counts */
+
+/* ---- VCF record writer --------------------------------------------------------------------------
+ * Replaces the per-variant cat(..., append=T) calls of bin/needlestack.r:396-413 (SNV), :549-567 (DEL), :712-730 (INS):
+ * same fields in the same order, numbers as R's cat() prints them under options(digits=7, scipen=100) (:153), the
+ * 3-bp CONT= context from an in-memory FASTA instead of two `samtools faidx` processes per variant (:389-394).
+ * Host code, multi-threaded.  `out` is the HOST result of ns_call_snv on the planes of `t` (ns_vcf_format_snv) or of
+ * ns_call_units on the indel units of `t` (ns_vcf_format_indel) with every emitted plane and emit_unit present; one
+ * record per emitted row, in row order.  sample_names: n strings (the POSSIBLE_CONTAMINATION_FROM_ text, :372-373). */
+typedef struct ns_fasta ns_fasta;
+typedef struct ns_vcf_text ns_vcf_text;
+ns_fasta *ns_fasta_load(const char *path); /* NULL when the file cannot be read */
+void ns_fasta_free(ns_fasta *fa);
+ns_vcf_text *ns_vcf_format_snv(const ns_table *t, const ns_out *out, const char *const *sample_names, const ns_fasta *fa,
+                               double gq_threshold, int n_threads);
+ns_vcf_text *ns_vcf_format_indel(const ns_table *t, const ns_out *out, const char *const *sample_names,
+                                 const ns_fasta *fa, double gq_threshold, int n_threads);
+const char *ns_vcf_text_data(const ns_vcf_text *v);
+size_t ns_vcf_text_size(const ns_vcf_text *v);
+const int64_t *ns_vcf_text_offsets(const ns_vcf_text *v); /* [records + 1]: record e = data[off[e] .. off[e+1]) */
+void ns_vcf_text_free(ns_vcf_text *v);
+/* one number as the writer prints it; na_as_nan != 0: NaN prints as "NaN" (a 0/0 of the reference), else "NA";
+ * returns the length of the full text */
+int ns_vcf_format_number(double x, int na_as_nan, char *buf, size_t buflen);
 
 /* ---- one workload over several GPUs from one host process -------------------------------------
  * Replaces the reference's region split + final merge: `--nsplit` / bin/bed_cut.r:19-58 cut the BED into pieces, one

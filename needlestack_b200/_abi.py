@@ -59,6 +59,7 @@ class NsOut(C.Structure):
         + [("gt", c_bp), ("status", c_bp), ("pooled", c_dp)]
         + [(k, C.c_int64) for k in ("n_fitted", "n_gated", "n_skipped")]
         + [(k, C.c_uint64) for k in ("n_seed", "n_lattice", "n_quad")]
+        + [("row_sigma", c_dp), ("row_slope", c_dp), ("row_max_gq", c_dp), ("row_flags", c_up)]
     )
 
 

@@ -85,6 +85,20 @@ def load_library():
     L.ns_table_chrom_name.argtypes = [vp, C.c_int]
     L.ns_table_indel_seq.restype = C.c_char_p
     L.ns_table_indel_seq.argtypes = [vp, C.c_int64]
+    L.ns_fasta_load.restype = vp
+    L.ns_fasta_load.argtypes = [C.c_char_p]
+    L.ns_fasta_free.argtypes = [vp]
+    for name in ("ns_vcf_format_snv", "ns_vcf_format_indel"):
+        getattr(L, name).restype = vp
+        getattr(L, name).argtypes = [vp, C.POINTER(NsOut), C.POINTER(C.c_char_p), vp, C.c_double, C.c_int]
+    L.ns_vcf_text_data.restype = vp
+    L.ns_vcf_text_data.argtypes = [vp]
+    L.ns_vcf_text_size.restype = C.c_size_t
+    L.ns_vcf_text_size.argtypes = [vp]
+    L.ns_vcf_text_offsets.restype = vp
+    L.ns_vcf_text_offsets.argtypes = [vp]
+    L.ns_vcf_text_free.argtypes = [vp]
+    L.ns_vcf_format_number.argtypes = [C.c_double, C.c_int, C.c_char_p, C.c_size_t]
     if L.ns_abi_version() != _abi.NS_ABI_VERSION:
         raise NeedlestackError("libns_b200.so ABI version mismatch")
     _LIB = L
@@ -96,6 +110,8 @@ EXPORTED_SYMBOLS = ("ns_abi_version", "ns_sizeof", "ns_params_glm_default", "ns_
                     "ns_call_snv", "ns_call_snv_u16", "ns_call_snv_device", "ns_call_units", "ns_glmrob_nb", "ns_qvalue_grid", "ns_measure_fp64_peak",
                     "ns_create_multi", "ns_destroy_multi", "ns_multi_devices", "ns_multi_last_error", "ns_multi_call_snv",
                     "ns_multi_call_snv_u16", "ns_multi_get_timings",
+                    "ns_fasta_load", "ns_fasta_free", "ns_vcf_format_snv", "ns_vcf_format_indel", "ns_vcf_text_data",
+                    "ns_vcf_text_size", "ns_vcf_text_offsets", "ns_vcf_text_free", "ns_vcf_format_number",
                     "ns_table_parse", "ns_table_free", "ns_table_positions", "ns_table_samples",
                     "ns_table_counts_pinned", "ns_table_counts", "ns_table_ref", "ns_table_ref_text", "ns_table_loc",
                     "ns_table_chrom", "ns_table_n_chrom", "ns_table_chrom_name", "ns_table_indel_cov",
@@ -197,6 +213,51 @@ def _ptr(a):
     return None if a is None else a.ctypes.data_as(C.c_void_p)
 
 
+def result_as_out(R):
+    """ns_out view of a Result (host arrays) for the VCF writer; keeps the arrays alive through the returned tuple"""
+    o = NsOut()
+    keep = []
+
+    def setp(field, key, typ):
+        a = np.ascontiguousarray(R[key])
+        keep.append(a)
+        setattr(o, field, a.ctypes.data_as(typ))
+
+    for k in ("pvalue", "qvalue", "gq", "qval_minaf", "sor", "rvsb", "fs", "pooled"):
+        setp(k, k, c_dp)
+    for k in ("sigma", "slope", "max_gq", "row_sigma", "row_slope", "row_max_gq"):
+        if k in R:
+            setp(k, k, c_dp)
+    for k in ("flags", "row_flags"):
+        if k in R:
+            setp(k, k, c_up)
+    setp("emit_unit", "emit_unit", c_lp)
+    setp("gt", "gt", c_bp)
+    setp("status", "status", c_bp)
+    o.n_emitted = int(R["n_emitted"])
+    o.emit_cap = int(R["n_emitted"])
+    return o, keep
+
+
+def vcf_records(table, R, names, fasta=None, gq_threshold=50.0, indel=False, n_threads=0):
+    """VCF record text (bytes) of every emitted row of R, formatted by the C++ writer (ns_vcf_format_snv / _indel), and
+    the [records + 1] offsets of the records in it"""
+    L = load_library()
+    o, keep = result_as_out(R)
+    arr = (C.c_char_p * len(names))(*[nm.encode() for nm in names])
+    fn = L.ns_vcf_format_indel if indel else L.ns_vcf_format_snv
+    h = fn(table._h, C.byref(o), arr, fasta, float(gq_threshold), int(n_threads) or (os.cpu_count() or 1))
+    if not h:
+        raise NeedlestackError("VCF writer: result planes missing")
+    try:
+        size = L.ns_vcf_text_size(h)
+        text = C.string_at(L.ns_vcf_text_data(h), size)
+        off = np.frombuffer(C.string_at(L.ns_vcf_text_offsets(h), 8 * (int(R["n_emitted"]) + 1)), dtype=np.int64).copy()
+    finally:
+        L.ns_vcf_text_free(h)
+    return text, off
+
+
 class Caller:
     """One GPU context (ns_ctx).  Not thread-safe; one per device and host thread."""
 
@@ -267,18 +328,20 @@ class Caller:
         return v.value
 
     # -- output allocation ---------------------------------------------------------------
-    def _alloc_out(self, U, n, emit_cap, want_rows=True):
+    def _alloc_out(self, U, n, emit_cap, want_rows=True, per_unit=True):
         o = NsOut()
         B = self._buf
-        a = dict(sigma=B("sigma", (U,), np.float64), slope=B("slope", (U,), np.float64),
-                 max_gq=B("max_gq", (U,), np.float64), flags=B("flags", (U,), np.uint32),
-                 iters=B("iters", (U,), np.uint32), emit_index=B("emit_index", (U,), np.int32),
-                 unit_cycles=B("unit_cycles", (U,), np.uint64))
-        o.sigma, o.slope, o.max_gq = (a[k].ctypes.data_as(c_dp) for k in ("sigma", "slope", "max_gq"))
-        o.flags = a["flags"].ctypes.data_as(c_up)
-        o.iters = a["iters"].ctypes.data_as(c_up)
-        o.emit_index = a["emit_index"].ctypes.data_as(c_ip)
-        o.unit_cycles = a["unit_cycles"].ctypes.data_as(C.POINTER(C.c_uint64))
+        a = {}
+        if per_unit:
+            a = dict(sigma=B("sigma", (U,), np.float64), slope=B("slope", (U,), np.float64),
+                     max_gq=B("max_gq", (U,), np.float64), flags=B("flags", (U,), np.uint32),
+                     iters=B("iters", (U,), np.uint32), emit_index=B("emit_index", (U,), np.int32),
+                     unit_cycles=B("unit_cycles", (U,), np.uint64))
+            o.sigma, o.slope, o.max_gq = (a[k].ctypes.data_as(c_dp) for k in ("sigma", "slope", "max_gq"))
+            o.flags = a["flags"].ctypes.data_as(c_up)
+            o.iters = a["iters"].ctypes.data_as(c_up)
+            o.emit_index = a["emit_index"].ctypes.data_as(c_ip)
+            o.unit_cycles = a["unit_cycles"].ctypes.data_as(C.POINTER(C.c_uint64))
         o.emit_cap = emit_cap if want_rows else 0
         if want_rows:
             for k in ("pvalue", "qvalue", "gq", "qval_minaf", "sor", "rvsb", "fs"):
@@ -291,6 +354,11 @@ class Caller:
             o.pooled = a["pooled"].ctypes.data_as(c_dp)
             a["emit_unit"] = B("emit_unit", (emit_cap,), np.int64)
             o.emit_unit = a["emit_unit"].ctypes.data_as(c_lp)
+            for k in ("row_sigma", "row_slope", "row_max_gq"):
+                a[k] = B(k, (emit_cap,), np.float64)
+                setattr(o, k, a[k].ctypes.data_as(c_dp))
+            a["row_flags"] = B("row_flags", (emit_cap,), np.uint32)
+            o.row_flags = a["row_flags"].ctypes.data_as(c_up)
         return o, a
 
     @staticmethod
@@ -298,7 +366,7 @@ class Caller:
         E = int(o.n_emitted)
         if want_rows:
             for k in ("pvalue", "qvalue", "gq", "qval_minaf", "sor", "rvsb", "fs", "gt", "status", "pooled",
-                      "emit_unit"):
+                      "emit_unit", "row_sigma", "row_slope", "row_max_gq", "row_flags"):
                 a[k] = a[k][:E]
         a.update(n_emitted=E, n_fitted=int(o.n_fitted), n_gated=int(o.n_gated), n_skipped=int(o.n_skipped),
                  n_seed=int(o.n_seed), n_lattice=int(o.n_lattice), n_quad=int(o.n_quad))
@@ -311,10 +379,10 @@ class Caller:
             return max(1024, U // 16)
         return U
 
-    def _run(self, fn, prm, U, n, emit_cap, want_rows):
+    def _run(self, fn, prm, U, n, emit_cap, want_rows, per_unit=True):
         cap = self._emit_cap(prm, U, emit_cap)
         while True:
-            o, a = self._alloc_out(U, n, cap, want_rows)
+            o, a = self._alloc_out(U, n, cap, want_rows, per_unit)
             rc = fn(o)
             if rc == _abi.NS_ERR_EMIT_OVERFLOW and emit_cap is None:
                 cap = int(o.n_emitted)
@@ -323,9 +391,11 @@ class Caller:
             return self._finish(o, a, want_rows)
 
     # -- the reference's per-allele SNV loop (needlestack.r:321-413) -----------------------
-    def call_snv(self, ref, counts, prm=None, emit_cap=None, want_rows=True, **kw):
+    def call_snv(self, ref, counts, prm=None, emit_cap=None, want_rows=True, per_unit=True, **kw):
         """ref uint8 [P] (0..3 = A,T,C,G), counts int32 [P][9][n] (depth,A,T,C,G,a,t,c,g), host arrays.  A uint16
-        `counts` array takes the narrow wire format (ns_call_snv_u16: half the host-to-device bytes)."""
+        `counts` array takes the narrow wire format (ns_call_snv_u16: half the host-to-device bytes).
+        per_unit=False: only the emitted rows come back (with row_sigma / row_slope / row_max_gq / row_flags per row):
+        what a caller that writes the VCF needs, without 44 B of device-to-host traffic for every gated unit."""
         prm = prm or make_params(**kw)
         u16 = getattr(counts, "dtype", None) == np.uint16
         counts = np.ascontiguousarray(counts, dtype=np.uint16 if u16 else np.int32)
@@ -335,7 +405,7 @@ class Caller:
             raise ValueError("counts must be [P][9][n] and ref [P]")
         fn = self._L.ns_call_snv_u16 if u16 else self._L.ns_call_snv
         return self._run(lambda o: fn(self._ctx, C.byref(prm), n, P, _ptr(ref), _ptr(counts), C.byref(o)),
-                         prm, 3 * P, n, emit_cap, want_rows)
+                         prm, 3 * P, n, emit_cap, want_rows, per_unit)
 
     def call_snv_device(self, d_ref_ptr, d_counts_ptr, P, n, prm, emit_cap=None, want_rows=True):
         """same with device-resident inputs (raw device pointers, e.g. torch tensor .data_ptr())"""
@@ -420,7 +490,7 @@ class MultiCaller(Caller):
         if rc != 0:
             raise NeedlestackError(f"ns error {rc}: {self._L.ns_multi_last_error(self._m).decode()}")
 
-    def call_snv(self, ref, counts, prm=None, emit_cap=None, want_rows=True, **kw):
+    def call_snv(self, ref, counts, prm=None, emit_cap=None, want_rows=True, per_unit=True, **kw):
         prm = prm or make_params(**kw)
         u16 = getattr(counts, "dtype", None) == np.uint16
         counts = np.ascontiguousarray(counts, dtype=np.uint16 if u16 else np.int32)
@@ -430,7 +500,7 @@ class MultiCaller(Caller):
             raise ValueError("counts must be [P][9][n] and ref [P]")
         fn = self._L.ns_multi_call_snv_u16 if u16 else self._L.ns_multi_call_snv
         return self._run(lambda o: fn(self._m, C.byref(prm), n, P, _ptr(ref), _ptr(counts), C.byref(o)),
-                         prm, 3 * P, n, emit_cap, want_rows)
+                         prm, 3 * P, n, emit_cap, want_rows, per_unit)
 
     def timings(self):
         """per device slot: the ns_timings of its context in the last call plus chunks pulled and host-thread wall ms"""

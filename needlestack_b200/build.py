@@ -8,7 +8,7 @@ ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libns_b200.so")
-SOURCES = [os.path.join(CSRC, f) for f in ("ns_api.cu", "ns_multi.cu", "ns_k_gate.cu", "ns_k_fit.cu", "ns_k_post.cu", "ns_table.cpp")]
+SOURCES = [os.path.join(CSRC, f) for f in ("ns_api.cu", "ns_multi.cu", "ns_k_gate.cu", "ns_k_fit.cu", "ns_k_post.cu", "ns_table.cpp", "ns_vcf.cpp")]
 DEPS = SOURCES + [os.path.join(CSRC, f) for f in ("ns_math.cuh", "ns_quad.cuh", "ns_core.cuh", "ns_fit.cuh", "ns_kernels.cuh", "ns_coop.cuh", "ns_logtab.h", "ns_hostmerge.hpp", "ns_api_internal.hpp")] + [
     os.path.join(ROOT, "include", "ns_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC"]

@@ -44,7 +44,8 @@
 /* ---- page-locked growable host planes ----------------------------------------------------------- */
 void HostRows::release()
 {
-    double **dpl[] = {&p.pvalue, &p.qvalue, &p.gq, &p.qval_minaf, &p.sor, &p.rvsb, &p.fs, &p.pooled};
+    double **dpl[] = {&p.pvalue, &p.qvalue, &p.gq, &p.qval_minaf, &p.sor, &p.rvsb, &p.fs, &p.pooled,
+                      &p.row_sigma, &p.row_slope, &p.row_max_gq};
     for (double **d : dpl) {
         if (*d)
             cudaFreeHost(*d);
@@ -56,8 +57,11 @@ void HostRows::release()
         cudaFreeHost(p.status);
     if (p.emit_unit)
         cudaFreeHost(p.emit_unit);
+    if (p.row_flags)
+        cudaFreeHost(p.row_flags);
     p.gt = p.status = nullptr;
     p.emit_unit = nullptr;
+    p.row_flags = nullptr;
     cap = 0;
 }
 
@@ -81,6 +85,8 @@ bool HostRows::reserve(int64_t rows, int n_samples, int64_t keep)
     al((void **)&q.qval_minaf, want * rb), al((void **)&q.sor, want * rb), al((void **)&q.rvsb, want * rb);
     al((void **)&q.fs, want * rb), al((void **)&q.gt, want * (size_t)n_samples), al((void **)&q.status, want * (size_t)n_samples);
     al((void **)&q.pooled, want * 8 * sizeof(double)), al((void **)&q.emit_unit, want * sizeof(int64_t));
+    al((void **)&q.row_sigma, want * sizeof(double)), al((void **)&q.row_slope, want * sizeof(double));
+    al((void **)&q.row_max_gq, want * sizeof(double)), al((void **)&q.row_flags, want * sizeof(uint32_t));
     if (!ok) {
         HostRows tmp;
         tmp.p = q;
@@ -102,20 +108,32 @@ RowSink ns_sink_from_out(ns_out *out)
     s.p.pvalue = out->pvalue, s.p.qvalue = out->qvalue, s.p.gq = out->gq, s.p.qval_minaf = out->qval_minaf;
     s.p.sor = out->sor, s.p.rvsb = out->rvsb, s.p.fs = out->fs, s.p.gt = out->gt, s.p.status = out->status;
     s.p.pooled = out->pooled, s.p.emit_unit = out->emit_unit;
+    s.p.row_sigma = out->row_sigma, s.p.row_slope = out->row_slope, s.p.row_max_gq = out->row_max_gq;
+    s.p.row_flags = out->row_flags;
     s.cap = out->emit_cap;
     s.want_rows = out->pvalue || out->qvalue || out->gq || out->qval_minaf || out->sor || out->rvsb || out->fs ||
-                  out->gt || out->status || out->pooled || out->emit_unit;
+                  out->gt || out->status || out->pooled || out->emit_unit || out->row_sigma || out->row_slope ||
+                  out->row_max_gq || out->row_flags;
     return s;
 }
 
-/* grant a kernel its dynamic shared memory once per size (the attribute call was re-issued for every chunk) */
+/* Grant a kernel its dynamic shared memory: the attribute belongs to the FUNCTION on a device, not to a context, and
+ * setting it again with a smaller size lowers it - so the largest size granted so far is kept per (device, kernel)
+ * for the whole process and only ever raised (it was re-issued for every chunk before). */
+#include <mutex>
+static std::mutex g_smem_mu;
+static size_t g_smem_set[64][8];
 template <class K> static cudaError_t ns_need_smem(ns_ctx *ctx, int slot, K kern, size_t bytes)
 {
-    if (bytes <= 48 * 1024 || bytes <= ctx->smem_set[slot])
+    if (bytes <= 48 * 1024)
+        return cudaSuccess;
+    std::lock_guard<std::mutex> lk(g_smem_mu);
+    size_t &have = g_smem_set[ctx->device & 63][slot];
+    if (bytes <= have)
         return cudaSuccess;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
     if (e == cudaSuccess)
-        ctx->smem_set[slot] = bytes;
+        have = bytes;
     return e;
 }
 
@@ -832,6 +850,13 @@ static int ns_pool_finish(ns_ctx *ctx, const ns_params &dprm, const double *qtab
         if (out->unit_cycles)
             out->unit_cycles[u] = h_cycles[i];
     }
+    if (sink->want_rows)
+        for (int i = 0; i < M; i++) { /* staging row i = pool slot i */
+            pl.h_rows.p.row_sigma[i] = h_sigma[i];
+            pl.h_rows.p.row_slope[i] = h_slope[i];
+            pl.h_rows.p.row_max_gq[i] = h_maxgq[i];
+            pl.h_rows.p.row_flags[i] = h_flags[i] & ~NS_F_POOLED;
+        }
     /* emitted rows: the pooled units that emit, in unit order, each with the number of rows that precede it */
     std::vector<ns_late_row> late;
     for (int i = 0; i < M; i++)
@@ -1036,11 +1061,10 @@ static int ns_run_chunk(ns_ctx *ctx, const ns_params &dprm, const double *qtab, 
         ctx->packed_cap = cap;
     }
     {
-        int wpb = 8;
-        int blocks = (U + wpb - 1) / wpb;
+        int blocks = (U + 255) / 256;
         if (blocks > ctx->sm_count * 8)
             blocks = ctx->sm_count * 8;
-        k_pack<<<blocks, wpb * 32, 0, st>>>(n, U, u_off, *emit_off, (int)ctx->packed_cap, ua, ctx->rows.view(),
+        k_pack<<<blocks, 256, 0, st>>>(n, U, u_off, *emit_off, (int)ctx->packed_cap, ua, ctx->rows.view(),
                                             ctx->packed.view(), ctx->emit_unit.p, ctx->emit_index_out.p, pl.lightpos.p,
                                             ctx->counters.p);
         CK(cudaGetLastError());
@@ -1074,6 +1098,10 @@ static int ns_run_chunk(ns_ctx *ctx, const ns_params &dprm, const double *qtab, 
         D2H(sp.status ? sp.status + eo * n : nullptr, pk.status, m, uint8_t);
         D2H(sp.pooled ? sp.pooled + eo * 8 : nullptr, pk.pooled, (size_t)n_copy * 8, double);
         D2H(sp.emit_unit ? sp.emit_unit + eo : nullptr, ctx->emit_unit.p, n_copy, int64_t);
+        D2H(sp.row_sigma ? sp.row_sigma + eo : nullptr, pk.rsigma, n_copy, double);
+        D2H(sp.row_slope ? sp.row_slope + eo : nullptr, pk.rslope, n_copy, double);
+        D2H(sp.row_max_gq ? sp.row_max_gq + eo : nullptr, pk.rmaxgq, n_copy, double);
+        D2H(sp.row_flags ? sp.row_flags + eo : nullptr, pk.rflags, n_copy, uint32_t);
     }
 #undef D2H
     CK(cudaEventRecord(ctx->ev[6], st));
@@ -1507,8 +1535,7 @@ int ns_qvalue_grid(ns_ctx *ctx, double sigma, double slope, int n, const int32_t
     CK(cudaMemcpyAsync(ctx->in_rows[1].p, ma_count, (size_t)n * sizeof(int32_t), cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(ctx->in_rows[2].p, gx, (size_t)m * sizeof(int32_t), cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(ctx->in_rows[3].p, gy, (size_t)m * sizeof(int32_t), cudaMemcpyHostToDevice, st));
-    if (sm > 48 * 1024)
-        CK(cudaFuncSetAttribute(k_qgrid, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    CK(ns_need_smem(ctx, 5, k_qgrid, sm));
     int blocks = (int)((m + 255) / 256);
     if (blocks > 2 * ctx->sm_count)
         blocks = 2 * ctx->sm_count;

@@ -38,27 +38,31 @@ template <class T> struct DevBuf {
 };
 
 struct PlaneSet {
-    DevBuf<double> pvalue, qvalue, gq, qval_minaf, sor, rvsb, fs, pooled;
+    DevBuf<double> pvalue, qvalue, gq, qval_minaf, sor, rvsb, fs, pooled, rsigma, rslope, rmaxgq;
     DevBuf<uint8_t> gt, status;
+    DevBuf<uint32_t> rflags;
     cudaError_t reserve(size_t rows, int n)
     {
         cudaError_t e;
         size_t m = rows * (size_t)n;
         if ((e = pvalue.reserve(m)) || (e = qvalue.reserve(m)) || (e = gq.reserve(m)) || (e = qval_minaf.reserve(m)) ||
             (e = sor.reserve(m)) || (e = rvsb.reserve(m)) || (e = fs.reserve(m)) || (e = pooled.reserve(rows * 8)) ||
-            (e = gt.reserve(m)) || (e = status.reserve(m)))
+            (e = gt.reserve(m)) || (e = status.reserve(m)) || (e = rsigma.reserve(rows)) || (e = rslope.reserve(rows)) ||
+            (e = rmaxgq.reserve(rows)) || (e = rflags.reserve(rows)))
             return e;
         return cudaSuccess;
     }
     ns_planes view()
     {
-        ns_planes v = {pvalue.p, qvalue.p, gq.p, qval_minaf.p, sor.p, rvsb.p, fs.p, pooled.p, gt.p, status.p};
+        ns_planes v = {pvalue.p, qvalue.p, gq.p, qval_minaf.p, sor.p, rvsb.p, fs.p, pooled.p, gt.p, status.p,
+                       rsigma.p, rslope.p, rmaxgq.p, rflags.p};
         return v;
     }
     void release()
     {
         pvalue.release(), qvalue.release(), gq.release(), qval_minaf.release(), sor.release(), rvsb.release(),
-            fs.release(), pooled.release(), gt.release(), status.release();
+            fs.release(), pooled.release(), gt.release(), status.release(), rsigma.release(), rslope.release(),
+            rmaxgq.release(), rflags.release();
     }
 };
 
@@ -155,8 +159,6 @@ struct ns_ctx {
     ns_counters *h_counters = nullptr; /* pinned */
     int *h_started = nullptr, *d_started = nullptr; /* mapped pinned flag written by k_fit_heavy */
     int64_t chunk_units = 0;           /* 0 = auto */
-    /* largest dynamic shared-memory size already granted to each kernel (cudaFuncSetAttribute once, not per chunk) */
-    size_t smem_set[8] = {};
     int64_t n_skipped_call = 0;
 };
 

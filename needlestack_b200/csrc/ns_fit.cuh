@@ -926,6 +926,11 @@ NS_GFN double ns_irls_step(double sig, const ns_work &w, int n, double maxmu, co
     return beta;
 }
 
+#if defined(NS_FIT_TRACE) && !defined(__CUDA_ARCH__)
+static thread_local double *ns_fit_trace_sig = nullptr, *ns_fit_trace_beta = nullptr;
+static thread_local int ns_fit_trace_cap = 0;
+#endif
+
 /* The fit proper: glm_rob_nb.r:58-205 on the samples with w.x[i] > 0.
  * Expects w.y / w.x filled (x <= 0 for samples outside the fit); maxmu = max(x) over ALL
  * samples of the unit (:20). */
@@ -1109,6 +1114,12 @@ NS_GF inline void ns_fit_unit(const ns_work &w, int n, double maxmu, const ns_pa
         res.cnt.quad_err = 0;
         beta11 = beta1;
         len11 = len1;
+#if defined(NS_FIT_TRACE) && !defined(__CUDA_ARCH__)
+        if (ns_fit_trace_sig && it < ns_fit_trace_cap) { /* tests/emul only: the iterates of the alternation */
+            ns_fit_trace_sig[it] = sig;
+            ns_fit_trace_beta[it] = beta1;
+        }
+#endif
         it++;
     }
     if (G::any(res.cnt.quad_overflow))

@@ -17,6 +17,8 @@ struct ns_row_planes {
     uint8_t *gt, *status;                                        /* [rows][n] */
     double *pooled;                                              /* [rows][8] */
     int64_t *emit_unit;                                          /* [rows] */
+    double *row_sigma, *row_slope, *row_max_gq;                  /* [rows] */
+    uint32_t *row_flags;                                         /* [rows] */
 };
 
 /* copy `count` consecutive rows s[from..] -> d[to..]; planes missing on either side are skipped; overlapping ranges
@@ -41,6 +43,10 @@ static inline void ns_rows_copy(const ns_row_planes &d, int64_t to, const ns_row
     NS_MV(status, cb);
     NS_MV(pooled, 8 * sizeof(double));
     NS_MV(emit_unit, sizeof(int64_t));
+    NS_MV(row_sigma, sizeof(double));
+    NS_MV(row_slope, sizeof(double));
+    NS_MV(row_max_gq, sizeof(double));
+    NS_MV(row_flags, sizeof(uint32_t));
 #undef NS_MV
 }
 

@@ -528,53 +528,66 @@ __global__ void k_scan_total(const int *flag, const int *excl, int n, int *total
         *total = n > 0 ? excl[n - 1] + flag[n - 1] : 0;
 }
 
-/* rows of emitted units, in unit order, into the packed planes; units whose fit runs in the call-wide pool only
- * record how many emitted rows precede them (their insertion point at the end of the call); counts the skipped
- * positions' units on the way */
+/* Rows of the emitted units, in unit order, into the packed planes.  One THREAD per unit does the bookkeeping (row
+ * index or -1, skipped-position count, insertion point of a unit whose fit runs in the call-wide pool) with coalesced
+ * accesses - a WGS-like chunk has millions of units and a few hundred emitted rows - and the warp then copies the rows
+ * of its emitting lanes together. */
 __global__ void k_pack(int n, int n_units, int64_t u0, int64_t emit_off, int cap, ns_unit_arrays ua,
                        ns_planes src, ns_planes dst, int64_t *emit_unit, int *emit_index_out, int64_t *pool_lightpos,
                        ns_counters *cnt)
 {
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int wpb = blockDim.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const unsigned FULL = 0xffffffffu;
     int n_skip = 0;
-    for (int u = blockIdx.x * wpb + warp; u < n_units; u += gridDim.x * wpb) {
-        const uint32_t fl = ua.flags[u];
-        n_skip += (fl & NS_F_SKIPPED) != 0;
-        if (fl & NS_F_POOLED) {
-            if (lane == 0) {
+    const int stride = gridDim.x * blockDim.x;
+    for (int base = blockIdx.x * blockDim.x + threadIdx.x - lane; base < n_units; base += stride) {
+        const int u = base + lane;
+        int d = 0, row = 0;
+        bool copy = false;
+        if (u < n_units) {
+            const uint32_t fl = ua.flags[u];
+            n_skip += (fl & NS_F_SKIPPED) != 0;
+            if (fl & NS_F_POOLED) {
                 pool_lightpos[ua.row[u]] = emit_off + ua.emitidx[u];
                 emit_index_out[u] = -1;
-            }
-            continue;
-        }
-        if (!ua.emitflag[u]) {
-            if (lane == 0)
+            } else if (!ua.emitflag[u]) {
                 emit_index_out[u] = -1;
-            continue;
+            } else {
+                d = ua.emitidx[u];
+                emit_index_out[u] = (int)(emit_off + d);
+                copy = d < cap;
+                row = ua.row[u];
+            }
         }
-        const int d = ua.emitidx[u];
-        if (lane == 0)
-            emit_index_out[u] = (int)(emit_off + d);
-        if (d >= cap)
-            continue;
-        const size_t so = (size_t)ua.row[u] * n, dof = (size_t)d * n;
-        for (int i = lane; i < n; i += 32) {
-            dst.pvalue[dof + i] = src.pvalue[so + i];
-            dst.qvalue[dof + i] = src.qvalue[so + i];
-            dst.gq[dof + i] = src.gq[so + i];
-            dst.qval_minaf[dof + i] = src.qval_minaf[so + i];
-            dst.sor[dof + i] = src.sor[so + i];
-            dst.rvsb[dof + i] = src.rvsb[so + i];
-            dst.fs[dof + i] = src.fs[so + i];
-            dst.gt[dof + i] = src.gt[so + i];
-            dst.status[dof + i] = src.status[so + i];
+        unsigned m = __ballot_sync(FULL, copy);
+        while (m) {
+            const int sl = __ffs(m) - 1;
+            m &= m - 1;
+            const int dd = __shfl_sync(FULL, d, sl), rr = __shfl_sync(FULL, row, sl), uu = base + sl;
+            const size_t so = (size_t)rr * n, dof = (size_t)dd * n;
+            for (int i = lane; i < n; i += 32) {
+                dst.pvalue[dof + i] = src.pvalue[so + i];
+                dst.qvalue[dof + i] = src.qvalue[so + i];
+                dst.gq[dof + i] = src.gq[so + i];
+                dst.qval_minaf[dof + i] = src.qval_minaf[so + i];
+                dst.sor[dof + i] = src.sor[so + i];
+                dst.rvsb[dof + i] = src.rvsb[so + i];
+                dst.fs[dof + i] = src.fs[so + i];
+                dst.gt[dof + i] = src.gt[so + i];
+                dst.status[dof + i] = src.status[so + i];
+            }
+            if (lane < 8)
+                dst.pooled[(size_t)dd * 8 + lane] = src.pooled[(size_t)rr * 8 + lane];
+            if (lane == 0) {
+                emit_unit[dd] = u0 + uu;
+                dst.rsigma[dd] = ua.sigma[uu];
+                dst.rslope[dd] = ua.slope[uu];
+                dst.rmaxgq[dd] = ua.max_gq[uu];
+                dst.rflags[dd] = ua.flags[uu];
+            }
         }
-        if (lane < 8)
-            dst.pooled[(size_t)d * 8 + lane] = src.pooled[(size_t)ua.row[u] * 8 + lane];
-        if (lane == 0)
-            emit_unit[d] = u0 + u;
     }
+    n_skip = __reduce_add_sync(FULL, n_skip);
     if (lane == 0 && n_skip)
         atomicAdd(&cnt->n_skipped, n_skip);
 }

@@ -35,6 +35,8 @@ struct ns_counters {
 struct ns_planes {
     double *pvalue, *qvalue, *gq, *qval_minaf, *sor, *rvsb, *fs, *pooled;
     uint8_t *gt, *status;
+    double *rsigma, *rslope, *rmaxgq; /* per row: the unit's sigma, slope, max(GQ) (packed planes only) */
+    uint32_t *rflags;
 };
 
 /* device side of the call-wide pool: the five count rows of every pooled unit (copied out of the chunk's input

@@ -6,10 +6,13 @@ mpileup2readcounts table on STDIN, `names.txt` in the working directory, VCF app
 What is kept from bin/needlestack.r: option names and defaults (:23-128), names.txt / pairs file
 handling (:155-185), the VCF header (:258-305), the order and content of every VCF field (:396-413,
 :549-567, :712-730), R's number formatting (`cat`: 7 significant digits, options(scipen=100)).
-What is different: the table is parsed in one pass (readcounts.load_table), all candidate alleles of a
-chunk go through the GPU batch API, and the 3-bp context comes from an in-memory FASTA instead of two
-`samtools faidx` processes per variant.  Plots (`--do_plots`, Gviz) are out of scope: `--do_plots`
-other than NONE is accepted and ignored with a warning.
+What is different: the table is read in blocks and parsed in one pass per block (readcounts.load_table, C++), all
+candidate alleles of a block go through the GPU batch API, the VCF records are formatted by the C++ writer of the
+library (ns_vcf_format_snv / _indel; `vcf_line` below is the same formatter in Python, kept as the executable
+specification the tests compare against), and the 3-bp context comes from an in-memory FASTA instead of two
+`samtools faidx` processes per variant.  Three stages overlap: a reader thread parses block k+1 while block k is on the
+GPU and the records of block k-1 are being written.  Plots (`--do_plots`, Gviz) are out of scope: `--do_plots` other
+than NONE is accepted and ignored with a warning.
 """
 import math
 import os
@@ -79,7 +82,8 @@ def parse_args(argv):
              min_af_extra_rob=num("min_af_extra_rob", 0.2), min_prop_extra_rob=num("min_prop_extra_rob", 0.1),
              max_prop_extra_rob=num("max_prop_extra_rob", 0.8), afmin_power=num("afmin_power", -1.0),
              sigma=num("sigma", 0.1), source_path=a.get("source_path", ""), device=int(a.get("device", 0)),
-             chunk=int(a.get("chunk_lines", 65536)))
+             chunk=int(a.get("chunk_lines", 0)), chunk_bytes=int(a.get("chunk_bytes", 256 << 20)),
+             writer=a.get("writer", "native"))
     if o["SB_type"] not in ("SOR", "RVSB", "FS"):
         raise SystemExit("SB_type must be SOR, RVSB or FS")
     return o
@@ -220,7 +224,7 @@ def vcf_line(chrom, pos, ref_txt, alt_txt, typ, row, dp, vp, vm, rp, rm, sigma, 
                                                             (";WARN=INV_REF" if inv else ""))
     with np.errstate(divide="ignore", invalid="ignore"):
         af_s = ma / dp
-    info = (f"TYPE={typ};NS={ns};AF={rfmt(float((gq >= thr).sum()) / ns if ns else float('nan'))};DP={rfmt(pooled[7])}"
+    info = (f"TYPE={typ};NS={ns};AF={rfmt(float((gq >= thr).sum()) / ns if ns else float('nan'), nan='NaN')};DP={rfmt(pooled[7])}"
             f";RO={rfmt(pooled[3] + pooled[4])};AO={rfmt(float(ma.sum()))};SRF={rfmt(pooled[3])};SRR={rfmt(pooled[4])}"
             f";SAF={rfmt(pooled[5])};SAR={rfmt(pooled[6])};SOR={rfmt(pooled[0])};RVSB={rfmt(pooled[1])}"
             f";FS={rfmt(pooled[2])};ERR={rfmt(slope)};SIG={rfmt(sigma)};CONT={before}x{after}{warn}")
@@ -266,7 +270,12 @@ def call_table(caller, T, o, names, pairs=None, fasta=None, caller_indel=None):
 
             indel_job = threading.Thread(target=run_indels)
             indel_job.start()
-    S = caller.call_snv(T.ref, T.counts, prm=prm)
+    native = o.get("writer", "native") == "native"
+    S = caller.call_snv(T.ref, T.counts, prm=prm, per_unit=not native)  # the C++ writer reads the per-row values
+    if native:
+        return _native_records(caller, T, S, o, names, fasta, prm, indel_job, box if indel_job is not None else None)
+    if isinstance(fasta, FastaHandle):
+        fasta = fasta.as_dict()
     recs = []  # (position row, order key, text)
     keys = ("gq", "qval_minaf", "sor", "rvsb", "fs", "gt", "status", "pooled")
     for e, u in enumerate(S.emit_unit):
@@ -310,7 +319,57 @@ def call_table(caller, T, o, names, pairs=None, fasta=None, caller_indel=None):
                            I.slope[u], int(I.flags[u]), I.max_gq[u], o, fasta, names, before, after)
             recs.append((p, 3 + int(T.indel_type[u]) * 100000 + u, txt))
     recs.sort(key=lambda r: (r[0], r[1]))
-    return [r[2] for r in recs]
+    return [r[2].encode() for r in recs]
+
+
+class FastaHandle:
+    """reference sequences loaded once by the library (ns_fasta_load) for the C++ VCF writer"""
+
+    def __init__(self, path):
+        self.path = path
+        self._L = api.load_library()
+        self.h = self._L.ns_fasta_load(path.encode())
+        if not self.h:
+            raise SystemExit("Error : cannot read --fasta_ref")
+
+    def as_dict(self):
+        return read_fasta(self.path)
+
+    def close(self):
+        if self.h:
+            self._L.ns_fasta_free(self.h)
+            self.h = None
+
+
+def _native_records(caller, T, S, o, names, fasta, prm, indel_job, box):
+    """the records of one table block from the C++ writer: SNV records come out in unit order (= input order); indel
+    records (deletions before insertions per line) are interleaved by position"""
+    fh = fasta.h if isinstance(fasta, FastaHandle) else None
+    thr = o["GQ_threshold"]
+    txt, off = api.vcf_records(T, S, names, fh, thr, indel=False)
+    if not len(T.indel_pos):
+        return [txt]
+    if indel_job is not None:
+        indel_job.join()
+        if "err" in box:
+            raise box["err"]
+        I = box["I"]
+    else:
+        dp, vp, vm, rp, rm, ind = T.indel_unit_rows()
+        I = caller.call_units(dp, vp, vm, rp, rm, is_indel=ind, prm=prm)
+    if I.n_emitted == 0:
+        return [txt]
+    itxt, ioff = api.vcf_records(T, I, names, fh, thr, indel=True)
+    su = np.asarray(S.emit_unit, dtype=np.int64)
+    iu = np.asarray(I.emit_unit, dtype=np.int64)
+    pos = np.concatenate([su // 3, T.indel_pos[iu]])
+    key = np.concatenate([su % 3, 3 + T.indel_type[iu].astype(np.int64) * 100000 + iu])
+    order = np.lexsort((key, pos))
+    ns_ = len(su)
+    out = []
+    for j in order:
+        out.append(txt[off[j]:off[j + 1]] if j < ns_ else itxt[ioff[j - ns_]:ioff[j - ns_ + 1]])
+    return out
 
 
 def main(argv=None, stdin=None):
@@ -325,19 +384,25 @@ def main(argv=None, stdin=None):
         pairs = read_pairs(o["pairs_file"], names)
         if o["afmin_power"] == -1:
             o["afmin_power"] = 0.01  # bin/needlestack.r:166
-    fasta = read_fasta(o["fasta_ref"]) if o["fasta_ref"] and os.path.exists(o["fasta_ref"]) else None
+    fasta = None
+    if o["fasta_ref"] and os.path.exists(o["fasta_ref"]):
+        fasta = FastaHandle(o["fasta_ref"]) if o["writer"] == "native" else read_fasta(o["fasta_ref"])
     src = (stdin or sys.stdin.buffer)
     header_line = src.readline()  # bin/needlestack.r:317
     if os.path.exists(o["out_file"]):
         os.remove(o["out_file"])
     n = len(names)
-    # a reader thread parses chunk k+1 (C++, outside the GIL) while chunk k is on the GPU; two tables in flight
+    # Three stages in flight: a reader thread cuts the input into blocks of whole lines and parses block k+1 (C++,
+    # outside the GIL) while block k is on the GPU, and a writer thread appends the records of block k-1.
     import queue
     import threading
     q = queue.Queue(maxsize=1)
+    wq = queue.Queue(maxsize=2)
 
-    def reader():
-        try:
+    def blocks():
+        """whole-line blocks of the table: --chunk_lines lines each (the reference reads line by line; a line count
+        makes the block boundaries independent of the text), else ~--chunk_bytes bytes read in one call"""
+        if o["chunk"] > 0:
             while True:
                 lines = []
                 for _ in range(o["chunk"]):
@@ -346,26 +411,68 @@ def main(argv=None, stdin=None):
                         break
                     lines.append(ln)
                 if not lines:
-                    break
-                q.put(readcounts.load_table(b"".join(lines), n, has_header=False))
+                    return
+                yield b"".join(lines)
+        else:
+            tail = b""
+            while True:
+                blk = src.read(o["chunk_bytes"])
+                if not blk:
+                    if tail:
+                        yield tail
+                    return
+                cut = blk.rfind(b"\n") + 1
+                if cut == 0:
+                    tail += blk
+                    continue
+                yield (tail + blk[:cut]) if tail else (blk[:cut] if cut < len(blk) else blk)
+                tail = blk[cut:]
+
+    def reader():
+        try:
+            for blk in blocks():
+                q.put(readcounts.load_table(blk, n, has_header=False))
             q.put(None)
         except BaseException as e:  # surfaced in the main thread
             q.put(e)
 
+    werr = []
+
+    def writer(out):
+        try:
+            while True:
+                recs = wq.get()
+                if recs is None:
+                    return
+                out.writelines(recs)
+        except BaseException as e:
+            werr.append(e)
+
     th = threading.Thread(target=reader, daemon=True)
-    with open(o["out_file"], "a") as out, api.Caller(o["device"]) as caller, api.Caller(o["device"]) as caller2:
-        out.write(vcf_header(o, names, pairs is not None))
+    with open(o["out_file"], "ab") as out, api.Caller(o["device"]) as caller, api.Caller(o["device"]) as caller2:
+        out.write(vcf_header(o, names, pairs is not None).encode())
+        wt = threading.Thread(target=writer, args=(out,), daemon=True)
         th.start()
-        while True:
-            T = q.get()
-            if T is None:
-                break
-            if isinstance(T, BaseException):
-                raise T
-            for txt in call_table(caller, T, o, names, pairs, fasta, caller_indel=caller2):
-                out.write(txt)
-            T.close()
+        wt.start()
+        try:
+            while True:
+                T = q.get()
+                if T is None:
+                    break
+                if isinstance(T, BaseException):
+                    raise T
+                wq.put(call_table(caller, T, o, names, pairs, fasta, caller_indel=caller2))
+                T.close()
+                if werr:
+                    raise werr[0]
+        finally:
+            wq.put(None)
+            wt.join()
+        if werr:
+            raise werr[0]
     th.join()
+    if isinstance(fasta, FastaHandle):
+        fasta.close()
     return 0
 
 

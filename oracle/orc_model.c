@@ -246,6 +246,11 @@ static double D_absmax(rvec u, rvec v)
     return fabs(m);
 }
 
+/* optional trace of the outer alternation (sigma and beta after every pass), for the divergence diagnostics of
+ * tests/test_chaotic_units.py; thread-local, set by orc_glmrob_nb_trace() */
+static __thread double *g_trace_sig = NULL, *g_trace_beta = NULL;
+static __thread int g_trace_cap = 0;
+
 int orc_glmrob_nb(int N, const double *y_in, const double *x_in, const orc_glm_params *prm,
                   double *pvalues, double *qvalues, double *gq, orc_glm_info *info)
 {
@@ -448,6 +453,10 @@ int orc_glmrob_nb(int N, const double *y_in, const double *x_in, const orc_glm_p
         if (st.quad_err)
             info->quad_error = 1; /* R would have stopped the script here */
         beta11 = beta1;
+        if (g_trace_sig && it < g_trace_cap) {
+            g_trace_sig[it] = sig;
+            g_trace_beta[it] = beta1.v[0];
+        }
         it++;
     }
     info->n_outer = it;
@@ -473,6 +482,20 @@ int orc_glmrob_nb(int N, const double *y_in, const double *x_in, const orc_glm_p
     free(x);
     free(removed);
     return 0;
+}
+
+int orc_glmrob_nb_trace(int N, const double *y, const double *x, const orc_glm_params *prm, int cap, double *sig_trace,
+                        double *beta_trace, orc_glm_info *info)
+{
+    double *p = (double *)malloc(sizeof(double) * 3 * (size_t)(N + 1));
+    g_trace_sig = sig_trace;
+    g_trace_beta = beta_trace;
+    g_trace_cap = cap;
+    int rc = orc_glmrob_nb(N, y, x, prm, p, p + N, p + 2 * N, info);
+    g_trace_sig = g_trace_beta = NULL;
+    g_trace_cap = 0;
+    free(p);
+    return rc;
 }
 
 /* ---- needlestack.r per-allele body -------------------------------------- */

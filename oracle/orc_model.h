@@ -38,6 +38,9 @@ void orc_glm_params_default(orc_glm_params *p); /* glmrob.nb's own defaults */
 /* glmrob.nb(y, x, ...) -> coverage/ma_count are the inputs; outputs length N */
 int orc_glmrob_nb(int N, const double *y, const double *x, const orc_glm_params *prm,
                   double *pvalues, double *qvalues, double *gq, orc_glm_info *info);
+/* same fit, recording sigma and beta after each of the first `cap` outer passes (test diagnostics) */
+int orc_glmrob_nb_trace(int N, const double *y, const double *x, const orc_glm_params *prm, int cap, double *sig_trace,
+                        double *beta_trace, orc_glm_info *info);
 
 /* caller-level parameters, needlestack.r:64-92 */
 typedef struct {

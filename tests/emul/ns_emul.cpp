@@ -4,6 +4,7 @@
  * that the control flow and numerics of the CUDA path can be checked against the oracle
  * on a machine without a GPU.  Never linked into libns_b200.so.
  */
+#define NS_FIT_TRACE 1
 #include "../../needlestack_b200/csrc/ns_core.cuh"
 #include <stdlib.h>
 #include <string.h>
@@ -82,6 +83,36 @@ int emul_unit(int n, const int32_t *dp, const int32_t *vp, const int32_t *vm, co
     *max_gq = mg;
     *flags_out = flags;
     return 0;
+}
+
+/* the iterates (sigma, beta after every outer pass) of the kernel's fit of one glmrob.nb(y, x) unit; fast != 0: the
+ * warp kernel's table / recurrence path; returns the number of outer passes */
+int emul_fit_trace(int n, const int32_t *y, const int32_t *x, int fast, const ns_params *prm, int cap, double *sig_trace,
+                   double *beta_trace)
+{
+    std::vector<double> buf(ns_work_doubles(n) + 16);
+    static double rtab[NS_RTAB];
+    for (int j = 1; j < NS_RTAB; j++)
+        rtab[j] = 1.0 / (double)j;
+    ns_work w;
+    ns_work_bind(w, buf.data(), n, rtab, ns_h_logtab);
+    double maxmu = -INFINITY;
+    for (int i = 0; i < n; i++) {
+        w.y[i] = (double)y[i];
+        w.x[i] = (double)x[i];
+        maxmu = fmax(maxmu, (double)x[i]);
+    }
+    ns_fit_trace_sig = sig_trace;
+    ns_fit_trace_beta = beta_trace;
+    ns_fit_trace_cap = cap;
+    ns_fit_result res;
+    if (fast)
+        ns_fit_unit<SerialG, 1>(w, n, maxmu, *prm, res);
+    else
+        ns_fit_unit<SerialG, 0>(w, n, maxmu, *prm, res);
+    ns_fit_trace_sig = ns_fit_trace_beta = nullptr;
+    ns_fit_trace_cap = 0;
+    return res.deferred ? -1 : res.n_outer;
 }
 
 /* numeric layer probes */

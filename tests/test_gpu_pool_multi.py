@@ -137,3 +137,24 @@ def test_multi_gpu_call_over_all_visible_devices(monkeypatch):
         B = m.call_snv(ref, counts, prm=make_params())
         assert sum(t["chunks"] for t in m.timings()) == 20
     _same(A, B, f"{nd} GPUs vs one")
+
+
+@pytest.mark.parametrize("multi", [False, True])
+def test_rows_only_call_returns_the_same_rows(monkeypatch, multi):
+    """per_unit=False (all per-unit output pointers NULL): the emitted rows are unchanged and carry their unit's sigma,
+    slope, max(GQ) and flags per row - including the rows that come from the pool and from other contexts"""
+    ref, counts = _batch(P=2400, seed=36)
+    monkeypatch.setenv("NS_CHUNK_UNITS", str(3 * 700))
+    monkeypatch.setenv("NS_MULTI_CHUNK_POSITIONS", "300")
+    mk = (lambda: ns.MultiCaller([0, 0])) if multi else (lambda: ns.Caller(0))
+    with mk() as c:
+        A = c.call_snv(ref, counts, prm=make_params())
+        B = c.call_snv(ref, counts, prm=make_params(), per_unit=False)
+    assert "sigma" not in B and "emit_index" not in B
+    assert A.n_emitted == B.n_emitted > 10 and A.n_fitted == B.n_fitted and A.n_skipped == B.n_skipped
+    for k in KEYS_ROWS:
+        assert np.array_equal(A[k], B[k], equal_nan=A[k].dtype.kind == "f"), k
+    for R in (A, B):
+        assert np.array_equal(R.row_sigma, A.sigma[A.emit_unit]) and np.array_equal(R.row_slope, A.slope[A.emit_unit])
+        assert np.array_equal(R.row_max_gq, A.max_gq[A.emit_unit]) and np.array_equal(R.row_flags, A.flags[A.emit_unit])
+    assert (A.flags[A.emit_unit] & ns.NS_F_GATE2).all()
