@@ -46,6 +46,9 @@ def parse():
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target CPU-baseline sample duration")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--rows-only", action="store_true",
+                    help="end-to-end leg asks for the emitted rows only (per-unit output pointers NULL: no per-unit D2H)")
+    ap.add_argument("--no-text", action="store_true", help="skip the text-table leg (loader and drop-in driver timings)")
     ap.add_argument("--p-germline", type=float, default=1e-4)
     ap.add_argument("--dump-cycles", default="")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
@@ -202,6 +205,54 @@ def cpu_oracle_rate(ref_np, counts_np, n_threads, target_s, prm_kw):
             Ps = Ps2
             dt, nf, O = run(Ps)
     return dict(value=nf / dt, fitted=nf, seconds=dt, positions=Ps, oracle=O)
+
+
+def text_leg(cfg, device, positions=16000, tile=12):
+    """The path either side of the kernels, timed on a C2-shaped TEXT table ("text-table parsing is timed
+    separately"): the columnar loader alone (ns_table_parse) and the whole drop-in driver - table text in, VCF text out
+    (block reader -> loader -> ns_call_snv -> C++ VCF writer, three stages overlapped).  The table holds `positions`
+    distinct synthetic positions written once and tiled `tile` times (writing 3.3 KB lines from Python is the slow part)."""
+    import io
+    import tempfile
+    from needlestack_b200 import driver, readcounts, synth
+    n = cfg.n
+    ref, counts = synth.generate(cfg, P=positions, seed=5)
+    cwd = os.getcwd()
+    d = tempfile.mkdtemp()
+    try:
+        os.chdir(d)
+        synth.write_table("t.tsv", ref, counts)
+        with open("names.txt", "w") as f:
+            f.write("".join(f"bam{i} S{i + 1}\n" for i in range(n)))
+        raw = open("t.tsv", "rb").read()
+        nl = raw.index(b"\n") + 1
+        text = raw[:nl] + raw[nl:] * tile
+        P = positions * tile
+        best = None
+        for _ in range(3):
+            t = time.perf_counter()
+            T = readcounts.load_table(text, n)
+            dt = time.perf_counter() - t
+            T.close()
+            best = dt if best is None else min(best, dt)
+        runs = []
+        nrec = 0
+        for _ in range(3):
+            t = time.perf_counter()
+            driver.main(["--out_file=out.vcf", f"--device={device}"], stdin=io.BytesIO(text))
+            runs.append(time.perf_counter() - t)
+        with open("out.vcf", "rb") as f:
+            nrec = sum(1 for ln in f if not ln.startswith(b"#"))
+        dt = min(runs[1:])
+        return {"table": f"{cfg.name}-shaped text, {n} samples x {P} positions ({positions} distinct, tiled x{tile}), "
+                         f"{len(text) / 1e9:.2f} GB", "loader_gbs": len(text) / 1e9 / best, "loader_s": best,
+                "loader_threads": os.cpu_count(), "driver_s": dt, "driver_gbs": len(text) / 1e9 / dt,
+                "driver_site_alleles_per_s": 3 * P / dt, "vcf_records": nrec,
+                "driver": "python -m needlestack_b200.driver (block reader, C++ loader, ns_call_snv, C++ VCF writer)"}
+    finally:
+        os.chdir(cwd)
+        import shutil
+        shutil.rmtree(d, ignore_errors=True)
 
 
 def parity_check(caller, ns, ref_np, counts_np, O, Ps):
@@ -512,7 +563,7 @@ def main():
         torch.cuda.synchronize()
 
         def step_host():
-            return caller.call_snv(h_ref.array, h_counts.array, prm=prm)
+            return caller.call_snv(h_ref.array, h_counts.array, prm=prm, per_unit=not a.rows_only)
 
         for _ in range(min(a.warmup, 3)):
             Rh = step_host()
@@ -528,11 +579,11 @@ def main():
         ms_h = allmax(ms_h_own)
         per_rank_ms_e2e = allgather(ms_h_own / a.steps)
         U = 3 * P
-        d2h = U * (8 + 8 + 8 + 4 + 4 + 4) + Rh.n_emitted * (n * 58 + 8 * 8 + 8)
+        d2h = (0 if a.rows_only else U * (8 + 8 + 8 + 4 + 4 + 4 + 8)) + Rh.n_emitted * (n * 58 + 8 * 8 + 8 + 28)
         e2e = {"value": allsum(fitted_h) / (ms_h * 1e-3), "unit": UNIT,
                "h2d_bytes_per_step": int(h_counts.nbytes + h_ref.nbytes), "d2h_bytes_per_step": int(d2h),
                "ms_per_step": ms_h / a.steps, "per_rank_ms": per_rank_ms_e2e,
-               "api": "needlestack_b200.Caller.call_snv -> ns_call_snv (C ABI)"}
+               "api": "needlestack_b200.Caller.call_snv -> ns_call_snv (C ABI)" + (", emitted rows only" if a.rows_only else "")}
         assert Rh.n_fitted == R.n_fitted and Rh.n_emitted == R.n_emitted
         ref_np = h_ref.array[: min(P, REF_SAMPLE_POSITIONS)].copy()
         counts_np = h_counts.array[: min(P, REF_SAMPLE_POSITIONS)].copy()
@@ -544,11 +595,11 @@ def main():
             torch.from_numpy(h16.array.view(np.int16)).copy_(d_counts.to(torch.int16))
             torch.cuda.synchronize()
             for _ in range(2):
-                R16 = caller.call_snv(h_ref.array, h16.array, prm=prm)
+                R16 = caller.call_snv(h_ref.array, h16.array, prm=prm, per_unit=not a.rows_only)
             barrier()
             e0.record()
             for _ in range(a.steps):
-                R16 = caller.call_snv(h_ref.array, h16.array, prm=prm)
+                R16 = caller.call_snv(h_ref.array, h16.array, prm=prm, per_unit=not a.rows_only)
             e1.record()
             barrier()
             ms16 = allmax(e0.elapsed_time(e1))
@@ -569,6 +620,12 @@ def main():
                          f"{r['seconds']:.1f} s), C oracle (restatement of glm_rob_nb.r/needlestack.r; R is not "
                          f"installed on this image), {ncores} pthreads"}
         parity_rep = parity_check(caller, ns, ref_np, counts_np, r["oracle"], r["positions"])
+    text = None
+    if rank == 0 and world == 1 and not a.no_text and not a.no_cpu:
+        try:
+            text = text_leg(cfg, local_rank)
+        except Exception as e:  # the headline does not depend on this leg
+            text = {"error": repr(e)[:300]}
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps,
                 "warmup": a.warmup, "ms_per_step": ms_max / a.steps, "higher_is_better": True, "scaling": "weak",
@@ -576,7 +633,7 @@ def main():
                 "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "roofline_gate": roofline_gate,
                 "cpu_baseline": cpu, "parity_check": parity_rep,
                 "per_rank_ms": per_rank_ms,
-                "detail": {"site_alleles_processed_per_s": units_all / (ms_max * 1e-3),
+                "detail": {"site_alleles_processed_per_s": units_all / (ms_max * 1e-3), "text": text,
                            "pool": {"units_per_step_rank0": tm_sum.get("pool_units", 0) / a.steps,
                                     "tail_ms_per_step_rank0": tm_sum.get("pool_tail_ms", 0) / a.steps,
                                     "chunks_per_step_rank0": tm_sum.get("chunks", 0) / a.steps},

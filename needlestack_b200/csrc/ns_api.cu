@@ -29,6 +29,7 @@
 #include "ns_hostmerge.hpp"
 #include "ns_api_internal.hpp"
 
+#define NS_GATE_SMEM_HDR 128
 #define CK(call)                                                                                   \
     do {                                                                                           \
         cudaError_t e_ = (call);                                                                   \
@@ -905,14 +906,57 @@ static int ns_run_chunk(ns_ctx *ctx, const ns_params &dprm, const double *qtab, 
     /* gate */
     CK(cudaEventRecord(ctx->ev[0], st));
     {
-        int blocks = (U + NS_WPB_GATE - 1) / NS_WPB_GATE;
-        int maxb = ctx->sm_count * 8;
-        if (blocks > maxb)
-            blocks = maxb;
-        size_t sm = (size_t)NS_WPB_GATE * n * sizeof(double);
-        CK(ns_need_smem(ctx, 2, k_gate, sm));
-        k_gate<<<blocks, NS_WPB_GATE * 32, sm, st>>>(src, dprm, u0_src, U, ua, ctx->counters.p);
-        CK(cudaGetLastError());
+        /* nobody reads the per-unit words of gated units when only rows are wanted and gated units cannot be emitted */
+        const int lean = !out->sigma && !out->slope && !out->max_gq && !out->iters && !out->unit_cycles &&
+                         dprm.emit_mode != NS_EMIT_ALL && !dprm.output_all_SNVs;
+        /* bulk-asynchronous staging for SNV planes (see ns_gate_staged): 16 or 8 positions per stage, 2-4 stages,
+         * at most ~96 KB per CTA so that two CTAs share an SM; needs 16-byte aligned planes */
+        int stage_k = 0, stages = 0, q_begin = 0;
+        const char *eg = getenv("NS_GATE_STAGED");
+        if (src.mode == 0 && !dprm.extra_rob && (u0_src % 3) == 0 && !(eg && atoi(eg) == 0)) {
+            const size_t pos_bytes = (size_t)36 * n;
+            const uintptr_t addr = (uintptr_t)(src.counts + (u0_src / 3) * 9 * (int64_t)n);
+            stage_k = 16 * pos_bytes <= 32 * 1024 ? 2 : (8 * pos_bytes <= 48 * 1024 ? 1 : 0);
+            if ((addr & 15) != 0 || U / 3 < 64 * NS_WPB_GATE)
+                stage_k = 0;
+            if (stage_k) {
+                const size_t sb = (size_t)stage_k * NS_WPB_GATE * pos_bytes;
+                stages = (int)((100 * 1024 - NS_GATE_SMEM_HDR) / sb);
+                stages = stages < 2 ? 2 : (stages > 4 ? 4 : stages);
+                const char *es = getenv("NS_GATE_STAGES");
+                if (es && atoi(es) >= 1 && atoi(es) <= 8)
+                    stages = atoi(es);
+                const size_t sms = NS_GATE_SMEM_HDR + (size_t)stages * sb;
+                if (sms > 200 * 1024) {
+                    stage_k = 0;
+                } else {
+                    const int PB = stage_k * NS_WPB_GATE;
+                    const int n_full = (U / 3) / PB;
+                    int per_sm = (int)((220 * 1024) / (sms + 1024));
+                    per_sm = per_sm > 2 ? 2 : (per_sm < 1 ? 1 : per_sm);
+                    int blocks = ctx->sm_count * per_sm;
+                    if (blocks > n_full)
+                        blocks = n_full;
+                    CK(ns_need_smem(ctx, 6, k_gate_staged, sms));
+                    k_gate_staged<<<blocks, NS_WPB_GATE * 32, sms, st>>>(src, dprm, u0_src, U, ua, ctx->counters.p, stage_k, stages,
+                                                                        n_full, lean);
+                    CK(cudaGetLastError());
+                    ctx->tm.kernel_launches++;
+                    q_begin = n_full * PB;
+                }
+            }
+        }
+        if (3 * (int64_t)q_begin < U) { /* everything (register-load form), or the positions behind the last whole block */
+            const int rest = U - 3 * q_begin;
+            size_t sm = (size_t)NS_WPB_GATE * n * sizeof(double);
+            int blocks = (rest + NS_WPB_GATE - 1) / NS_WPB_GATE;
+            int maxb = ctx->sm_count * 8;
+            if (blocks > maxb)
+                blocks = maxb;
+            CK(ns_need_smem(ctx, 2, k_gate, sm));
+            k_gate<<<blocks, NS_WPB_GATE * 32, sm, st>>>(src, dprm, u0_src, U, ua, ctx->counters.p, q_begin, lean);
+            CK(cudaGetLastError());
+        }
     }
     CK(cudaEventRecord(ctx->ev[1], st));
     /* rows for the units that need per-sample planes */

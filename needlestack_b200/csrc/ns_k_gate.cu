@@ -31,19 +31,23 @@ __device__ __forceinline__ bool ns_ratio_ge(int y, int x, double t)
 
 /* per-unit outputs of the gate (written by one lane) and the unit's work-list class, identical in
  * all lanes: bits 0-1 = 1 warp kernel, 2 cluster kernel, 0 none; bit 2 = needs result rows */
+/* lean: nobody reads the per-unit sigma / slope / max(GQ) / iteration words of a GATED unit (the caller asked for
+ * the emitted rows only and gated units cannot be emitted): 36 of the 48 bytes the gate writes per unit are skipped */
 __device__ __forceinline__ int ns_gate_commit(const ns_unit_arrays &ua, const ns_params &prm, int u, uint32_t flags,
-                                              int is_indel, double mu_hint, bool writer)
+                                              int is_indel, double mu_hint, bool writer, bool lean = false)
 {
     const bool gated = flags & NS_F_GATED, skipped = flags & NS_F_SKIPPED;
     const bool out_all = (!is_indel) && prm.output_all_SNVs;
     const bool need = !skipped && (!gated || prm.emit_mode == NS_EMIT_ALL || out_all);
     if (writer) {
         ua.flags[u] = flags;
-        ua.sigma[u] = NAN;
-        ua.slope[u] = NAN;
-        ua.max_gq[u] = 0.0;
-        ua.iters[u] = 0;
-        ua.cycles[u] = 0;
+        if (!(lean && gated)) {
+            ua.sigma[u] = NAN;
+            ua.slope[u] = NAN;
+            ua.max_gq[u] = 0.0;
+            ua.iters[u] = 0;
+            ua.cycles[u] = 0;
+        }
         ua.needrow[u] = need;
         ua.emitflag[u] = 0;
     }
@@ -103,29 +107,73 @@ __device__ __forceinline__ void ns_gate_insert(const int (&packed)[K], UOF u_of,
         ua.post_list[s_base[2] + off_p] = u;
 }
 
+/* SH: the position's planes sit in a shared-memory stage filled by cp.async.bulk (ns_gate_staged), else in global memory */
+template <int VEC, bool SH> struct ns_ldvec;
+template <> struct ns_ldvec<4, false> {
+    static __device__ __forceinline__ void ld(const int32_t *p, int *v)
+    {
+        const int4 t = __ldg(reinterpret_cast<const int4 *>(p));
+        v[0] = t.x;
+        v[1] = t.y;
+        v[2] = t.z;
+        v[3] = t.w;
+    }
+};
+template <> struct ns_ldvec<2, false> {
+    static __device__ __forceinline__ void ld(const int32_t *p, int *v)
+    {
+        const int2 t = __ldg(reinterpret_cast<const int2 *>(p));
+        v[0] = t.x;
+        v[1] = t.y;
+    }
+};
+template <> struct ns_ldvec<4, true> {
+    static __device__ __forceinline__ void ld(const int32_t *p, int *v)
+    {
+        const unsigned a = (unsigned)__cvta_generic_to_shared(p);
+        asm volatile("ld.shared.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]) : "r"(a));
+    }
+};
+template <> struct ns_ldvec<2, true> {
+    static __device__ __forceinline__ void ld(const int32_t *p, int *v)
+    {
+        const unsigned a = (unsigned)__cvta_generic_to_shared(p);
+        asm volatile("ld.shared.v2.s32 {%0, %1}, [%2];" : "=r"(v[0]), "=r"(v[1]) : "r"(a));
+    }
+};
+template <bool SH> __device__ __forceinline__ int ns_ld1(const int32_t *p)
+{
+    if (SH) {
+        int v;
+        const unsigned a = (unsigned)__cvta_generic_to_shared(p);
+        asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(a));
+        return v;
+    }
+    return __ldg(p);
+}
+
 /* Streaming gate for SNV planes without the extra-robust pre-filter (the caller's default):
  * warp = position; the depth row is scanned once for the three alleles; all tests are integer
  * compares and warp vote / reduce instructions; medians come from counts, not from a sort:
  *   median(x) < c  <=>  both middle order statistics < c  (count(x < c) decides, and when it equals
  *   n/2 for even n the two middle values are max{x < c} and min{x >= c}). */
-__device__ __forceinline__ int ns_gate_position(const ns_unit_src &src, const ns_params &prm, int64_t p, int u_first,
-                                                int n_units, const ns_unit_arrays &ua)
+template <bool SH>
+__device__ __forceinline__ int ns_gate_position(const int32_t *base, int n, int ref, const ns_params &prm, int u_first,
+                                                int n_units, const ns_unit_arrays &ua, bool lean)
 {
-    const int n = src.n, lane = threadIdx.x & 31;
+    const int lane = threadIdx.x & 31;
     const unsigned FULL = 0xffffffffu;
-    const int ref = src.ref[p];
     if (ref > 3) {
         if (lane < 3 && u_first + lane < n_units)
-            ns_gate_commit(ua, prm, u_first + lane, NS_F_SKIPPED | NS_F_GATED, 0, 0.0, true);
+            ns_gate_commit(ua, prm, u_first + lane, NS_F_SKIPPED | NS_F_GATED, 0, 0.0, true, lean);
         return 0;
     }
     int packed = 0;
-    const int32_t *base = src.counts + p * 9 * (int64_t)n;
     const double mc = prm.min_coverage;
     /* depth row: samples above min_coverage, order statistics around it, max depth */
     int n_cov = 0, n_less = 0, max_less = -1, min_geq = 0x7fffffff, maxx = 0;
     for (int i = lane; i < n; i += 32) {
-        const int x = base[i];
+        const int x = ns_ld1<SH>(base + i);
         n_cov += (double)x > mc;
         const bool less = (double)x < mc;
         n_less += less;
@@ -157,7 +205,7 @@ __device__ __forceinline__ int ns_gate_position(const ns_unit_src &src, const ns
         const int32_t *vp = base + (1 + alt) * (int64_t)n, *vm = base + (5 + alt) * (int64_t)n;
         int cnt_inv = 0, pos_a = 0, pos_r = 0, max_a = 0, max_r = 0, af_a = 0, af_r = 0;
         for (int i = lane; i < n; i += 32) {
-            const int x = base[i], ma = vp[i] + vm[i], rr = rp[i] + rm[i];
+            const int x = ns_ld1<SH>(base + i), ma = ns_ld1<SH>(vp + i) + ns_ld1<SH>(vm + i), rr = ns_ld1<SH>(rp + i) + ns_ld1<SH>(rm + i);
             cnt_inv += ns_ratio_gt(ma, x, 0.8);
             pos_a += ma > 0;
             pos_r += rr > 0;
@@ -181,8 +229,8 @@ __device__ __forceinline__ int ns_gate_position(const ns_unit_src &src, const ns
             float s = 0.f;
             int nf = 0;
             for (int i = lane; i < n; i += 32) {
-                const int x = base[i];
-                const int y = inv ? rp[i] + rm[i] : vp[i] + vm[i];
+                const int x = ns_ld1<SH>(base + i);
+                const int y = inv ? ns_ld1<SH>(rp + i) + ns_ld1<SH>(rm + i) : ns_ld1<SH>(vp + i) + ns_ld1<SH>(vm + i);
                 if (x > 0) {
                     s += __fdividef((float)y, (float)x);
                     nf++;
@@ -193,7 +241,7 @@ __device__ __forceinline__ int ns_gate_position(const ns_unit_src &src, const ns
             nf = __reduce_add_sync(FULL, nf);
             mu_hint = nf > 0 ? 1.001 * (double)s / (double)nf * (double)maxx : 0.0;
         }
-        packed |= ns_gate_commit(ua, prm, u, flags, 0, mu_hint, lane == 0) << (3 * k);
+        packed |= ns_gate_commit(ua, prm, u, flags, 0, mu_hint, lane == 0, lean) << (3 * k);
     }
     return packed;
 }
@@ -201,26 +249,24 @@ __device__ __forceinline__ int ns_gate_position(const ns_unit_src &src, const ns
 /* Same tests with the position's nine rows held in registers (n <= 32*R): all 9*R loads of a warp are
  * in flight at once (3.6 KB per warp at n = 100), which is what a streaming kernel needs to approach
  * the HBM rate; the per-base statistics are computed once and shared by the three alleles. */
-template <int R>
-__device__ __forceinline__ int ns_gate_position_reg(const ns_unit_src &src, const ns_params &prm, int64_t p,
-                                                    int u_first, int n_units, const ns_unit_arrays &ua)
+template <int R, bool SH>
+__device__ __forceinline__ int ns_gate_position_reg(const int32_t *base, int n, int ref, const ns_params &prm,
+                                                    int u_first, int n_units, const ns_unit_arrays &ua, bool lean)
 {
-    const int n = src.n, lane = threadIdx.x & 31;
+    const int lane = threadIdx.x & 31;
     const unsigned FULL = 0xffffffffu;
-    const int32_t *base = src.counts + p * 9 * (int64_t)n;
-    /* issue every load of the position (and the REF code) before anything depends on one of them */
+    /* issue every load of the position before anything depends on one of them */
     int v[9][R];
 #pragma unroll
     for (int r = 0; r < 9; r++)
 #pragma unroll
         for (int k = 0; k < R; k++) {
             const int i = lane + 32 * k;
-            v[r][k] = (i < n) ? __ldg(base + (int64_t)r * n + i) : 0;
+            v[r][k] = (i < n) ? ns_ld1<SH>(base + (int64_t)r * n + i) : 0;
         }
-    const int ref = src.ref[p];
     if (ref > 3) {
         if (lane < 3 && u_first + lane < n_units)
-            ns_gate_commit(ua, prm, u_first + lane, NS_F_SKIPPED | NS_F_GATED, 0, 0.0, true);
+            ns_gate_commit(ua, prm, u_first + lane, NS_F_SKIPPED | NS_F_GATED, 0, 0.0, true, lean);
         return 0;
     }
     int packed = 0;
@@ -298,7 +344,7 @@ __device__ __forceinline__ int ns_gate_position_reg(const ns_unit_src &src, cons
             const long long tot = (long long)__reduce_add_sync(FULL, (unsigned)NS_SEL4(sy, yb));
             mu_hint = sx > 0 ? 1.1 * (double)tot / (double)sx * (double)maxx : 0.0;
         }
-        packed |= ns_gate_commit(ua, prm, u, flags, 0, mu_hint, lane == 0) << (3 * k);
+        packed |= ns_gate_commit(ua, prm, u, flags, 0, mu_hint, lane == 0, lean) << (3 * k);
     }
 #undef NS_SEL4
     return packed;
@@ -313,34 +359,14 @@ __device__ __forceinline__ int ns_gate_position_reg(const ns_unit_src &src, cons
  *     eight store instructions per position instead of three copies and twenty-four single-lane stores).
  * ncu (profiles/): 987 -> ~430 warp instructions per position at n = 100; the kernel was issue-bound, not
  * HBM-bound, at 1.9 TB/s. */
-template <int VEC> struct ns_ldvec;
-template <> struct ns_ldvec<4> {
-    static __device__ __forceinline__ void ld(const int32_t *p, int *v)
-    {
-        const int4 t = __ldg(reinterpret_cast<const int4 *>(p));
-        v[0] = t.x;
-        v[1] = t.y;
-        v[2] = t.z;
-        v[3] = t.w;
-    }
-};
-template <> struct ns_ldvec<2> {
-    static __device__ __forceinline__ void ld(const int32_t *p, int *v)
-    {
-        const int2 t = __ldg(reinterpret_cast<const int2 *>(p));
-        v[0] = t.x;
-        v[1] = t.y;
-    }
-};
-
-template <int VEC>
-__device__ __forceinline__ int ns_gate_position_vec(const ns_unit_src &src, const ns_params &prm, int t_gt, int t_lt,
-                                                    int64_t p, int u_first, int n_units, const ns_unit_arrays &ua)
+template <int VEC, bool SH>
+__device__ __forceinline__ int ns_gate_position_vec(const int32_t *pos_base, int n, int ref, const ns_params &prm, int t_gt,
+                                                    int t_lt, int u_first, int n_units, const ns_unit_arrays &ua, bool lean)
 {
-    const int n = src.n, lane = threadIdx.x & 31;
+    const int lane = threadIdx.x & 31;
     const unsigned FULL = 0xffffffffu;
     const bool act = VEC * lane < n;
-    const int32_t *base = src.counts + p * 9 * (int64_t)n + VEC * lane;
+    const int32_t *base = pos_base + VEC * lane;
     int v[9][VEC];
 #pragma unroll
     for (int r = 0; r < 9; r++) {
@@ -348,12 +374,11 @@ __device__ __forceinline__ int ns_gate_position_vec(const ns_unit_src &src, cons
         for (int j = 0; j < VEC; j++)
             v[r][j] = 0;
         if (act)
-            ns_ldvec<VEC>::ld(base + (int64_t)r * n, v[r]);
+            ns_ldvec<VEC, SH>::ld(base + (int64_t)r * n, v[r]);
     }
-    const int ref = src.ref[p];
     if (ref > 3) {
         if (lane < 3 && u_first + lane < n_units)
-            ns_gate_commit(ua, prm, u_first + lane, NS_F_SKIPPED | NS_F_GATED, 0, 0.0, true);
+            ns_gate_commit(ua, prm, u_first + lane, NS_F_SKIPPED | NS_F_GATED, 0, 0.0, true, lean);
         return 0;
     }
     int n_cov = 0, n_less = 0, maxx = 0;
@@ -458,17 +483,133 @@ __device__ __forceinline__ int ns_gate_position_vec(const ns_unit_src &src, cons
     const double mu_hint = (!gate && sx > 0) ? 1.1 * (double)NS_SEL4(sy, yb) / (double)sx * (double)maxx : 0.0;
 #undef NS_SEL4
     const bool writer = lane < 3 && u_first + lane < n_units;
-    int cls = ns_gate_commit(ua, prm, u_first + k, flags, 0, mu_hint, writer);
+    int cls = ns_gate_commit(ua, prm, u_first + k, flags, 0, mu_hint, writer, lean);
     cls = writer ? cls << (3 * lane) : 0;
     return (int)__reduce_or_sync(FULL, (unsigned)cls);
 }
 
+/* one position through the form that fits n and the alignment of its planes; SH: planes in a shared-memory stage */
+template <bool SH>
+__device__ __forceinline__ int ns_gate_dispatch(const int32_t *base, int n, int ref, int vec, const ns_params &prm, int t_gt,
+                                                int t_lt, int u_first, int n_units, const ns_unit_arrays &ua, bool lean)
+{
+    if (vec == 4)
+        return ns_gate_position_vec<4, SH>(base, n, ref, prm, t_gt, t_lt, u_first, n_units, ua, lean);
+    if (vec == 2)
+        return ns_gate_position_vec<2, SH>(base, n, ref, prm, t_gt, t_lt, u_first, n_units, ua, lean);
+    if (n <= 64)
+        return ns_gate_position_reg<2, SH>(base, n, ref, prm, u_first, n_units, ua, lean);
+    if (n <= 128)
+        return ns_gate_position_reg<4, SH>(base, n, ref, prm, u_first, n_units, ua, lean);
+    return ns_gate_position<SH>(base, n, ref, prm, u_first, n_units, ua, lean);
+}
+
+/* ---- bulk-asynchronous staging (sm_90+: cp.async.bulk + mbarrier) -----------------------------------------------
+ * The planes of K * NS_WPB_GATE consecutive positions are one contiguous piece of global memory (36 n bytes per
+ * position).  One thread asks the copy engine for the whole piece with ONE cp.async.bulk per stage; completion is
+ * counted in bytes on the stage's mbarrier; the warps wait on the barrier and read their positions from shared
+ * memory.  `stages` pieces per CTA are in flight while one is being consumed, whatever n is - with register
+ * loads the bytes in flight shrank with n (3.6 TB/s at n = 50 against 5.0 TB/s at n = 100) and every 16 bytes cost a
+ * load instruction plus its address arithmetic in an issue-bound kernel. */
+__device__ __forceinline__ void ns_mbar_init(uint64_t *bar, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void ns_mbar_wait(uint64_t *bar, unsigned parity)
+{
+    asm volatile("{\n\t.reg .pred p;\n\tNS_WAIT:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t@p bra NS_DONE;\n\t"
+                 "bra NS_WAIT;\n\tNS_DONE:\n\t}" ::"r"((unsigned)__cvta_generic_to_shared(bar)),
+                 "r"(parity)
+                 : "memory");
+}
+/* arm the barrier with the byte count, then hand the copy to the async proxy (issued by one thread) */
+__device__ __forceinline__ void ns_bulk_load(void *smem_dst, const void *gmem_src, unsigned bytes, uint64_t *bar)
+{
+    const unsigned b = (unsigned)__cvta_generic_to_shared(bar), d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(d),
+                 "l"(gmem_src), "r"(bytes), "r"(b)
+                 : "memory");
+}
+
+#define NS_GATE_SMEM_HDR 128 /* mbarriers in front of the 128-byte aligned stages */
+
+template <int K>
+__device__ __forceinline__ void ns_gate_staged(const ns_unit_src &src, const ns_params &prm, int64_t p_first, int n_full_blocks,
+                                               int n_units, int stages, int vec, int t_gt, int t_lt, bool lean,
+                                               const ns_unit_arrays &ua, ns_counters *cnt)
+{
+    constexpr int PB = K * NS_WPB_GATE;
+    const int n = src.n;
+    const int warp = threadIdx.x >> 5;
+    const size_t pos_ints = (size_t)9 * n;
+    const unsigned stage_bytes = (unsigned)(PB * pos_ints * sizeof(int32_t));
+    uint64_t *bar = reinterpret_cast<uint64_t *>(ns_smem);
+    char *stage0 = reinterpret_cast<char *>(ns_smem) + NS_GATE_SMEM_HDR;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < stages; s++)
+            ns_mbar_init(bar + s, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        for (int s = 0; s < stages; s++) {
+            const int blk = blockIdx.x + s * gridDim.x;
+            if (blk < n_full_blocks)
+                ns_bulk_load(stage0 + (size_t)s * stage_bytes, src.counts + (p_first + (int64_t)blk * PB) * pos_ints, stage_bytes, bar + s);
+        }
+    }
+    __syncthreads();
+    int it = 0;
+    for (int blk = blockIdx.x; blk < n_full_blocks; blk += gridDim.x, it++) {
+        const int s = it % stages;
+        const unsigned parity = (unsigned)(it / stages) & 1u;
+        int refc[K];
+#pragma unroll
+        for (int j = 0; j < K; j++)
+            refc[j] = src.ref[p_first + (int64_t)blk * PB + j * NS_WPB_GATE + warp]; /* issued before the wait */
+        ns_mbar_wait(bar + s, parity);
+        const int32_t *st = reinterpret_cast<const int32_t *>(stage0 + (size_t)s * stage_bytes);
+        int packed[K];
+#pragma unroll
+        for (int j = 0; j < K; j++) {
+            const int q = blk * PB + j * NS_WPB_GATE + warp; /* position within the chunk */
+            packed[j] = ns_gate_dispatch<true>(st + (size_t)(j * NS_WPB_GATE + warp) * pos_ints, n, refc[j], vec, prm, t_gt, t_lt,
+                                               3 * q, n_units, ua, lean);
+        }
+        /* the list insertion is a CTA collective with barriers: behind it every warp has finished reading the stage */
+        ns_gate_insert<K>(packed, [&](int j) { return 3 * (blk * PB + j * NS_WPB_GATE + warp); }, n_units, ua, cnt);
+        const int nxt = blk + stages * gridDim.x;
+        if (threadIdx.x == 0 && nxt < n_full_blocks)
+            ns_bulk_load(stage0 + (size_t)s * stage_bytes, src.counts + (p_first + (int64_t)nxt * PB) * pos_ints, stage_bytes, bar + s);
+    }
+}
+
+/* The bulk-asynchronous form of the gate for whole blocks of stage_k * 8 positions of SNV planes (positions of a stage
+ * are 36 n bytes apart: 16-byte aligned rows when n % 4 == 0, 8-byte aligned when n is even); the positions behind
+ * the last whole block are left to k_gate(q_begin).  Two CTAs per SM (shared memory bounds the occupancy, so the
+ * kernel may use up to 128 registers).  lean: see ns_gate_commit. */
+__global__ void __launch_bounds__(NS_WPB_GATE * 32, 2)
+k_gate_staged(ns_unit_src src, ns_params prm, int64_t u0, int n_units, ns_unit_arrays ua, ns_counters *cnt, int stage_k,
+              int stages, int n_full_blocks, int lean_i)
+{
+    const int n = src.n;
+    const double mcv = prm.min_coverage;
+    const int t_gt = mcv < 0 ? -1 : (int)floor(mcv), t_lt = mcv <= 0 ? 0 : (int)ceil(mcv);
+    const bool small_mc = mcv < 2.0e9;
+    const int vec_s = (small_mc && (n & 3) == 0 && n > 32 && n <= 128) ? 4 : (small_mc && (n & 1) == 0 && n > 16 && n <= 64) ? 2 : 0;
+    if (stage_k == 2)
+        ns_gate_staged<2>(src, prm, u0 / 3, n_full_blocks, n_units, stages, vec_s, t_gt, t_lt, lean_i != 0, ua, cnt);
+    else
+        ns_gate_staged<1>(src, prm, u0 / 3, n_full_blocks, n_units, stages, vec_s, t_gt, t_lt, lean_i != 0, ua, cnt);
+}
+
+/* q_begin: first position of the chunk this launch handles (the whole blocks before it went through k_gate_staged);
+ * lean: see ns_gate_commit */
 __global__ void __launch_bounds__(NS_WPB_GATE * 32, 4)
-k_gate(ns_unit_src src, ns_params prm, int64_t u0, int n_units, ns_unit_arrays ua, ns_counters *cnt)
+k_gate(ns_unit_src src, ns_params prm, int64_t u0, int n_units, ns_unit_arrays ua, ns_counters *cnt, int q_begin, int lean_i)
 {
     const int n = src.n;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int wstride = gridDim.x * NS_WPB_GATE;
+    const bool lean = lean_i != 0;
     if (src.mode == 0 && !prm.extra_rob && (u0 % 3) == 0) {
         /* fast path: warp = position (uniform trip count per CTA: the list insertion is a CTA collective) */
         const int n_pos = (n_units + 2) / 3;
@@ -476,27 +617,21 @@ k_gate(ns_unit_src src, ns_params prm, int64_t u0, int n_units, ns_unit_arrays u
         const double mcv = prm.min_coverage;
         const int t_gt = mcv < 0 ? -1 : (int)floor(mcv), t_lt = mcv <= 0 ? 0 : (int)ceil(mcv);
         const bool small_mc = mcv < 2.0e9;
-        const uintptr_t addr = (uintptr_t)src.counts;
+        const uintptr_t addr = (uintptr_t)(src.counts + (u0 / 3) * 9 * (int64_t)n);
         const int vec = (small_mc && (n & 3) == 0 && n > 32 && n <= 128 && (addr & 15) == 0) ? 4
                         : (small_mc && (n & 1) == 0 && n > 16 && n <= 64 && (addr & 7) == 0) ? 2 : 0;
         constexpr int K = 4; /* positions per warp between two list insertions */
-        for (int q0 = blockIdx.x * NS_WPB_GATE * K; q0 < n_pos; q0 += wstride * K) {
+        for (int q0 = q_begin + blockIdx.x * NS_WPB_GATE * K; q0 < n_pos; q0 += wstride * K) {
             int packed[K];
 #pragma unroll 1
             for (int j = 0; j < K; j++) {
                 const int q = q0 + j * NS_WPB_GATE + warp;
                 int pk = 0;
                 if (q < n_pos) {
-                    if (vec == 4)
-                        pk = ns_gate_position_vec<4>(src, prm, t_gt, t_lt, u0 / 3 + q, 3 * q, n_units, ua);
-                    else if (vec == 2)
-                        pk = ns_gate_position_vec<2>(src, prm, t_gt, t_lt, u0 / 3 + q, 3 * q, n_units, ua);
-                    else if (n <= 64)
-                        pk = ns_gate_position_reg<2>(src, prm, u0 / 3 + q, 3 * q, n_units, ua);
-                    else if (n <= 128)
-                        pk = ns_gate_position_reg<4>(src, prm, u0 / 3 + q, 3 * q, n_units, ua);
-                    else
-                        pk = ns_gate_position(src, prm, u0 / 3 + q, 3 * q, n_units, ua);
+                    const int64_t p = u0 / 3 + q;
+                    const int32_t *base = src.counts + p * 9 * (int64_t)n;
+                    /* vector forms: the loads are in flight before the REF code is needed */
+                    pk = ns_gate_dispatch<false>(base, n, src.ref[p], vec, prm, t_gt, t_lt, 3 * q, n_units, ua, lean);
                 }
 #pragma unroll
                 for (int t = 0; t < K; t++)
@@ -515,7 +650,7 @@ k_gate(ns_unit_src src, ns_params prm, int64_t u0, int n_units, ns_unit_arrays u
             ns_rows r = ns_unit_rows(src, u0 + u);
             double mu_hint = 0;
             uint32_t flags = ns_gate_unit<WarpG>(r, n, prm, src.plain, scratch, &mu_hint);
-            packed = ns_gate_commit(ua, prm, u, flags, r.is_indel, mu_hint, lane == 0);
+            packed = ns_gate_commit(ua, prm, u, flags, r.is_indel, mu_hint, lane == 0, lean);
         }
         const int pk1[1] = {packed};
         ns_gate_insert<1>(pk1, [&](int) { return u; }, n_units, ua, cnt);

@@ -12,7 +12,7 @@ import numpy as np
 from needlestack_b200 import driver, synth
 
 P = int(sys.argv[1]) if len(sys.argv) > 1 else 120000
-chunk = int(sys.argv[2]) if len(sys.argv) > 2 else 30000
+chunk = int(sys.argv[2]) if len(sys.argv) > 2 else 0
 cfg = synth.CONFIGS["C2"]
 ref, counts = synth.generate(cfg, P=P, seed=5)
 d = tempfile.mkdtemp()
