@@ -475,7 +475,7 @@ def main():
     fp64_peak = caller.fp64_peak_tflops()
 
     def step_device():
-        return caller.call_snv_device(d_ref.data_ptr(), d_counts.data_ptr(), P, n, prm)
+        return caller.call_snv_device(d_ref.data_ptr(), d_counts.data_ptr(), P, n, prm, per_unit=not a.rows_only)
 
     # ---- device-resident leg ----
     for _ in range(a.warmup):

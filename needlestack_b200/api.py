@@ -407,11 +407,11 @@ class Caller:
         return self._run(lambda o: fn(self._ctx, C.byref(prm), n, P, _ptr(ref), _ptr(counts), C.byref(o)),
                          prm, 3 * P, n, emit_cap, want_rows, per_unit)
 
-    def call_snv_device(self, d_ref_ptr, d_counts_ptr, P, n, prm, emit_cap=None, want_rows=True):
+    def call_snv_device(self, d_ref_ptr, d_counts_ptr, P, n, prm, emit_cap=None, want_rows=True, per_unit=True):
         """same with device-resident inputs (raw device pointers, e.g. torch tensor .data_ptr())"""
         return self._run(lambda o: self._L.ns_call_snv_device(self._ctx, C.byref(prm), n, P, C.c_void_p(d_ref_ptr),
                                                               C.c_void_p(d_counts_ptr), C.byref(o)),
-                         prm, 3 * P, n, emit_cap, want_rows)
+                         prm, 3 * P, n, emit_cap, want_rows, per_unit)
 
     # -- explicit units: indel alleles, annotate_vcf, batched glmrob.nb ---------------------
     def call_units(self, dp, vp, vm=None, rp=None, rm=None, is_indel=None, plain=False, prm=None, emit_cap=None,

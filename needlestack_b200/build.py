@@ -50,7 +50,10 @@ def build(force=False, verbose=False):
     if failed:
         raise RuntimeError("nvcc failed building libns_b200.so")
     tmp = LIB + ".tmp"
-    r = subprocess.run([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", tmp] + objs,
+    # CUDA runtime: linked statically by default (nvcc's default; the library then has no run-time dependency on a
+    # libcudart.so of the right version).  NS_CUDART=shared links libcudart.so instead (found through the rpath below).
+    cudart = ["-cudart", "shared", "-Xlinker", "-rpath=/usr/local/cuda/lib64"] if os.environ.get("NS_CUDART") == "shared" else []
+    r = subprocess.run([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", tmp] + cudart + objs,
                        capture_output=True, text=True)
     if r.returncode != 0:
         sys.stderr.write(r.stdout + r.stderr)

@@ -913,7 +913,10 @@ static int ns_run_chunk(ns_ctx *ctx, const ns_params &dprm, const double *qtab, 
          * at most ~96 KB per CTA so that two CTAs share an SM; needs 16-byte aligned planes */
         int stage_k = 0, stages = 0, q_begin = 0;
         const char *eg = getenv("NS_GATE_STAGED");
-        if (src.mode == 0 && !dprm.extra_rob && (u0_src % 3) == 0 && !(eg && atoi(eg) == 0)) {
+        /* measured on B200 (profiles/README.md, round 2): 0.53 of the HBM copy rate at n = 100 against 0.74 for the
+         * register-load form - the kernel is bound by instruction issue and the register file already holds as many
+         * bytes in flight as the stages do - so the staged form is opt-in (NS_GATE_STAGED=1) */
+        if (src.mode == 0 && !dprm.extra_rob && (u0_src % 3) == 0 && eg && atoi(eg) == 1) {
             const size_t pos_bytes = (size_t)36 * n;
             const uintptr_t addr = (uintptr_t)(src.counts + (u0_src / 3) * 9 * (int64_t)n);
             stage_k = 16 * pos_bytes <= 32 * 1024 ? 2 : (8 * pos_bytes <= 48 * 1024 ? 1 : 0);
@@ -953,8 +956,16 @@ static int ns_run_chunk(ns_ctx *ctx, const ns_params &dprm, const double *qtab, 
             int maxb = ctx->sm_count * 8;
             if (blocks > maxb)
                 blocks = maxb;
-            CK(ns_need_smem(ctx, 2, k_gate, sm));
-            k_gate<<<blocks, NS_WPB_GATE * 32, sm, st>>>(src, dprm, u0_src, U, ua, ctx->counters.p, q_begin, lean);
+            const int form = ns_gate_form(src.mode, dprm.extra_rob, u0_src, n, dprm.min_coverage,
+                                          src.mode == 0 ? src.counts + (u0_src / 3) * 9 * (int64_t)n : nullptr);
+            if (form == 4) {
+                k_gate_v4<<<blocks, NS_WPB_GATE * 32, 0, st>>>(src, dprm, u0_src, U, ua, ctx->counters.p, q_begin, lean);
+            } else if (form == 2) {
+                k_gate_v2<<<blocks, NS_WPB_GATE * 32, 0, st>>>(src, dprm, u0_src, U, ua, ctx->counters.p, q_begin, lean);
+            } else {
+                CK(ns_need_smem(ctx, 2, k_gate, sm));
+                k_gate<<<blocks, NS_WPB_GATE * 32, sm, st>>>(src, dprm, u0_src, U, ua, ctx->counters.p, q_begin, lean);
+            }
             CK(cudaGetLastError());
         }
     }

@@ -359,15 +359,13 @@ __device__ __forceinline__ int ns_gate_position_reg(const int32_t *base, int n, 
  *     eight store instructions per position instead of three copies and twenty-four single-lane stores).
  * ncu (profiles/): 987 -> ~430 warp instructions per position at n = 100; the kernel was issue-bound, not
  * HBM-bound, at 1.9 TB/s. */
+/* the position's nine rows, VEC consecutive samples per lane (zeros in the lanes beyond n) */
 template <int VEC, bool SH>
-__device__ __forceinline__ int ns_gate_position_vec(const int32_t *pos_base, int n, int ref, const ns_params &prm, int t_gt,
-                                                    int t_lt, int u_first, int n_units, const ns_unit_arrays &ua, bool lean)
+__device__ __forceinline__ void ns_gate_load_vec(const int32_t *pos_base, int n, int (&v)[9][VEC])
 {
     const int lane = threadIdx.x & 31;
-    const unsigned FULL = 0xffffffffu;
     const bool act = VEC * lane < n;
     const int32_t *base = pos_base + VEC * lane;
-    int v[9][VEC];
 #pragma unroll
     for (int r = 0; r < 9; r++) {
 #pragma unroll
@@ -376,6 +374,21 @@ __device__ __forceinline__ int ns_gate_position_vec(const int32_t *pos_base, int
         if (act)
             ns_ldvec<VEC, SH>::ld(base + (int64_t)r * n, v[r]);
     }
+}
+
+/* The gate of one position from its rows in registers.  The kernel is bound by instruction issue, not by HBM, so the
+ * warp reductions are packed: the two coverage counts share one REDUX (16 bits each: n <= 128), the four inversion
+ * counts another (8 bits each), the yes/no facts (some count > 0, some count >= min_reads, some value >= 2^28) one
+ * OR-reduction; the sums that only feed the cluster-path prediction are reduced only when a unit of the position
+ * passes the gate (3 reductions per position instead of 16 for the gated majority). */
+template <int VEC>
+__device__ __forceinline__ int ns_gate_compute_vec(const int (&v)[9][VEC], int n, int ref, const ns_params &prm, int t_gt,
+                                                   int t_lt, int t_reads, int u_first, int n_units,
+                                                   const ns_unit_arrays &ua, bool lean)
+{
+    const int lane = threadIdx.x & 31;
+    const unsigned FULL = 0xffffffffu;
+    const bool act = VEC * lane < n;
     if (ref > 3) {
         if (lane < 3 && u_first + lane < n_units)
             ns_gate_commit(ua, prm, u_first + lane, NS_F_SKIPPED | NS_F_GATED, 0, 0.0, true, lean);
@@ -395,16 +408,12 @@ __device__ __forceinline__ int ns_gate_position_vec(const int32_t *pos_base, int
         n_cov = 0;
         n_less = 0;
     }
-    n_cov = __reduce_add_sync(FULL, n_cov);
-    n_less = __reduce_add_sync(FULL, n_less);
-    maxx = __reduce_max_sync(FULL, maxx);
-    sx = __reduce_add_sync(FULL, sx);
     /* per base: #(y/x > 0.8) (needlestack.r:330: exactly 5y > 4x for integers, see ns_gate_position_reg; 0/0 and the
      * zeros of lanes beyond n are false), max(y), sum(y).  sum(y > 0) == 0 (glm_rob_nb.r:38) is max(y) == 0.
      * Depths and counts below 2^28 (always, in practice) keep 4x - 5y in 32 bits. */
     int cinv[4], mx[4], afok[4];
     unsigned sy[4];
-    const bool wide = maxx >= (1 << 28);
+    unsigned cpack = 0, facts = 0;
 #pragma unroll
     for (int b = 0; b < 4; b++) {
         cinv[b] = mx[b] = afok[b] = 0;
@@ -416,24 +425,30 @@ __device__ __forceinline__ int ns_gate_position_vec(const int32_t *pos_base, int
             mx[b] = max(mx[b], y);
             sy[b] += (unsigned)y;
         }
+        cpack |= (unsigned)cinv[b] << (8 * b);
+        facts |= (mx[b] > 0 ? 1u : 0u) << b;
+        facts |= (mx[b] >= t_reads ? 1u : 0u) << (4 + b);
+        facts |= (mx[b] >= (1 << 28) ? 1u : 0u) << 8;
     }
+    facts |= (maxx >= (1 << 28) ? 1u : 0u) << 8;
     if (prm.min_af > 0) {
 #pragma unroll
-        for (int b = 0; b < 4; b++)
+        for (int b = 0; b < 4; b++) {
 #pragma unroll
             for (int j = 0; j < VEC; j++)
                 afok[b] |= ns_ratio_ge(v[1 + b][j] + v[5 + b][j], v[0][j], prm.min_af);
-#pragma unroll
-        for (int b = 0; b < 4; b++)
-            afok[b] = __any_sync(FULL, afok[b]);
+            facts |= (afok[b] ? 1u : 0u) << (9 + b);
+        }
     }
+    const unsigned cov = __reduce_add_sync(FULL, (unsigned)n_cov | ((unsigned)n_less << 16));
+    cpack = __reduce_add_sync(FULL, cpack);
+    facts = __reduce_or_sync(FULL, facts);
+    n_cov = (int)(cov & 0xffffu);
+    n_less = (int)(cov >> 16);
 #pragma unroll
-    for (int b = 0; b < 4; b++) {
-        cinv[b] = __reduce_add_sync(FULL, cinv[b]);
-        mx[b] = __reduce_max_sync(FULL, mx[b]);
-        sy[b] = __reduce_add_sync(FULL, sy[b]);
-    }
-    if (wide || max(max(mx[0], mx[1]), max(mx[2], mx[3])) >= (1 << 28)) {
+    for (int b = 0; b < 4; b++)
+        cinv[b] = (int)((cpack >> (8 * b)) & 0xffu);
+    if (facts & (1u << 8)) {
         /* depths or counts of 2^28 and more (the latter only in malformed input): the inversion test in 64 bits */
 #pragma unroll
         for (int b = 0; b < 4; b++) {
@@ -474,18 +489,43 @@ __device__ __forceinline__ int ns_gate_position_vec(const int32_t *pos_base, int
     const int alt = k + (k >= ref ? 1 : 0);
     const bool inv = (double)NS_SEL4(cinv, alt) > 0.5 * (double)n; /* needlestack.r:330 */
     const int yb = inv ? ref : alt;
-    const int maxy = NS_SEL4(mx, yb);
-    bool gate = pos_gate || (double)maxy < prm.min_reads || maxy == 0;
+    /* max(y) < min_reads (y integer: max(y) < ceil(min_reads)) or sum(y > 0) == 0, glm_rob_nb.r:38 */
+    bool gate = pos_gate || !((facts >> (4 + yb)) & 1u) || !((facts >> yb) & 1u);
     if (prm.min_af > 0)
-        gate = gate || !NS_SEL4(afok, yb);
+        gate = gate || !((facts >> (9 + yb)) & 1u);
     const uint32_t flags = (inv ? NS_F_REF_INV : 0u) | (gate ? NS_F_GATED : 0u);
-    /* pooled allelic fraction times the largest depth: first-fit mean of the deepest sample */
-    const double mu_hint = (!gate && sx > 0) ? 1.1 * (double)NS_SEL4(sy, yb) / (double)sx * (double)maxx : 0.0;
-#undef NS_SEL4
     const bool writer = lane < 3 && u_first + lane < n_units;
+    /* pooled allelic fraction times the largest depth = first-fit mean of the deepest sample: needed (and reduced)
+     * only when a unit of the position goes on to the fit */
+    double mu_hint = 0.0;
+    if (__any_sync(FULL, writer && !gate)) {
+        maxx = __reduce_max_sync(FULL, maxx);
+        sx = __reduce_add_sync(FULL, sx);
+#pragma unroll
+        for (int b = 0; b < 4; b++)
+            sy[b] = __reduce_add_sync(FULL, sy[b]);
+        mu_hint = (!gate && sx > 0) ? 1.1 * (double)NS_SEL4(sy, yb) / (double)sx * (double)maxx : 0.0;
+    }
+#undef NS_SEL4
     int cls = ns_gate_commit(ua, prm, u_first + k, flags, 0, mu_hint, writer, lean);
     cls = writer ? cls << (3 * lane) : 0;
     return (int)__reduce_or_sync(FULL, (unsigned)cls);
+}
+
+/* integer form of max(y) < min_reads for integer counts: max(y) >= t_reads passes */
+__device__ __forceinline__ int ns_gate_t_reads(const ns_params &prm)
+{
+    const double c = ceil(prm.min_reads);
+    return c <= 0.0 ? 0 : (c >= 2147483647.0 ? 2147483647 : (int)c);
+}
+
+template <int VEC, bool SH>
+__device__ __forceinline__ int ns_gate_position_vec(const int32_t *pos_base, int n, int ref, const ns_params &prm, int t_gt,
+                                                    int t_lt, int u_first, int n_units, const ns_unit_arrays &ua, bool lean)
+{
+    int v[9][VEC];
+    ns_gate_load_vec<VEC, SH>(pos_base, n, v);
+    return ns_gate_compute_vec<VEC>(v, n, ref, prm, t_gt, t_lt, ns_gate_t_reads(prm), u_first, n_units, ua, lean);
 }
 
 /* one position through the form that fits n and the alignment of its planes; SH: planes in a shared-memory stage */
@@ -601,26 +641,57 @@ k_gate_staged(ns_unit_src src, ns_params prm, int64_t u0, int n_units, ns_unit_a
         ns_gate_staged<1>(src, prm, u0 / 3, n_full_blocks, n_units, stages, vec_s, t_gt, t_lt, lean_i != 0, ua, cnt);
 }
 
-/* q_begin: first position of the chunk this launch handles (the whole blocks before it went through k_gate_staged);
- * lean: see ns_gate_commit */
-__global__ void __launch_bounds__(NS_WPB_GATE * 32, 4)
-k_gate(ns_unit_src src, ns_params prm, int64_t u0, int n_units, ns_unit_arrays ua, ns_counters *cnt, int q_begin, int lean_i)
+/* The gate over the positions q_begin .. of a chunk, one instantiation per load form so that each gets its own
+ * register allocation under the 64-register cap (four CTAs per SM):
+ *   FORM 4  n % 4 == 0, 32 < n <= 128, 16-byte aligned planes: nine 128-bit loads per lane
+ *   FORM 2  n even, 16 < n <= 64, 8-byte aligned: nine 64-bit loads per lane, the NEXT position's rows requested
+ *           before the current one is evaluated (a position is only 2.3 KB per warp: too little in flight otherwise)
+ *   FORM 0  everything else: scalar register / strided loads, explicit-unit sources, the extra-robust pre-filter
+ * The host picks the form with ns_gate_form() (same conditions). */
+template <int FORM>
+__device__ __forceinline__ void ns_gate_body(const ns_unit_src &src, const ns_params &prm, int64_t u0, int n_units,
+                                             const ns_unit_arrays &ua, ns_counters *cnt, int q_begin, bool lean)
 {
     const int n = src.n;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int wstride = gridDim.x * NS_WPB_GATE;
-    const bool lean = lean_i != 0;
     if (src.mode == 0 && !prm.extra_rob && (u0 % 3) == 0) {
         /* fast path: warp = position (uniform trip count per CTA: the list insertion is a CTA collective) */
         const int n_pos = (n_units + 2) / 3;
-        /* integer forms of the min_coverage tests; vector loads need aligned planes */
+        /* integer forms of the min_coverage tests */
         const double mcv = prm.min_coverage;
         const int t_gt = mcv < 0 ? -1 : (int)floor(mcv), t_lt = mcv <= 0 ? 0 : (int)ceil(mcv);
-        const bool small_mc = mcv < 2.0e9;
-        const uintptr_t addr = (uintptr_t)(src.counts + (u0 / 3) * 9 * (int64_t)n);
-        const int vec = (small_mc && (n & 3) == 0 && n > 32 && n <= 128 && (addr & 15) == 0) ? 4
-                        : (small_mc && (n & 1) == 0 && n > 16 && n <= 64 && (addr & 7) == 0) ? 2 : 0;
         constexpr int K = 4; /* positions per warp between two list insertions */
+        if (FORM == 2) {
+            const int t_reads = ns_gate_t_reads(prm);
+            for (int q0 = q_begin + blockIdx.x * NS_WPB_GATE * K; q0 < n_pos; q0 += wstride * K) {
+                int packed[K];
+                int va[9][2], vb[9][2];
+                int ra = 4, rb = 4;
+                {
+                    const int q = q0 + warp;
+                    if (q < n_pos) {
+                        ns_gate_load_vec<2, false>(src.counts + (u0 / 3 + q) * 9 * (int64_t)n, n, va);
+                        ra = src.ref[u0 / 3 + q];
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < K; j++) {
+                    const int q = q0 + j * NS_WPB_GATE + warp, qn = q + NS_WPB_GATE;
+                    int(&cur)[9][2] = (j & 1) ? vb : va;
+                    int(&nxt)[9][2] = (j & 1) ? va : vb;
+                    int &rcur = (j & 1) ? rb : ra;
+                    int &rnxt = (j & 1) ? ra : rb;
+                    if (j + 1 < K && qn < n_pos) {
+                        ns_gate_load_vec<2, false>(src.counts + (u0 / 3 + qn) * 9 * (int64_t)n, n, nxt);
+                        rnxt = src.ref[u0 / 3 + qn];
+                    }
+                    packed[j] = q < n_pos ? ns_gate_compute_vec<2>(cur, n, rcur, prm, t_gt, t_lt, t_reads, 3 * q, n_units, ua, lean) : 0;
+                }
+                ns_gate_insert<K>(packed, [&](int j) { return 3 * (q0 + j * NS_WPB_GATE + warp); }, n_units, ua, cnt);
+            }
+            return;
+        }
         for (int q0 = q_begin + blockIdx.x * NS_WPB_GATE * K; q0 < n_pos; q0 += wstride * K) {
             int packed[K];
 #pragma unroll 1
@@ -630,8 +701,11 @@ k_gate(ns_unit_src src, ns_params prm, int64_t u0, int n_units, ns_unit_arrays u
                 if (q < n_pos) {
                     const int64_t p = u0 / 3 + q;
                     const int32_t *base = src.counts + p * 9 * (int64_t)n;
-                    /* vector forms: the loads are in flight before the REF code is needed */
-                    pk = ns_gate_dispatch<false>(base, n, src.ref[p], vec, prm, t_gt, t_lt, 3 * q, n_units, ua, lean);
+                    /* vector form: the loads are in flight before the REF code is needed */
+                    if (FORM == 4)
+                        pk = ns_gate_position_vec<4, false>(base, n, src.ref[p], prm, t_gt, t_lt, 3 * q, n_units, ua, lean);
+                    else
+                        pk = ns_gate_dispatch<false>(base, n, src.ref[p], 0, prm, t_gt, t_lt, 3 * q, n_units, ua, lean);
                 }
 #pragma unroll
                 for (int t = 0; t < K; t++)
@@ -642,6 +716,8 @@ k_gate(ns_unit_src src, ns_params prm, int64_t u0, int n_units, ns_unit_arrays u
         }
         return;
     }
+    if (FORM != 0)
+        return; /* the host never launches a vector form for these sources */
     double *scratch = ns_smem + (size_t)warp * (size_t)n;
     for (int v0 = blockIdx.x * NS_WPB_GATE; v0 < n_units; v0 += wstride) {
         const int u = v0 + warp;
@@ -655,6 +731,24 @@ k_gate(ns_unit_src src, ns_params prm, int64_t u0, int n_units, ns_unit_arrays u
         const int pk1[1] = {packed};
         ns_gate_insert<1>(pk1, [&](int) { return u; }, n_units, ua, cnt);
     }
+}
+
+/* q_begin: first position of the chunk this launch handles (the whole blocks before it went through k_gate_staged);
+ * lean: see ns_gate_commit */
+__global__ void __launch_bounds__(NS_WPB_GATE * 32, 4)
+k_gate(ns_unit_src src, ns_params prm, int64_t u0, int n_units, ns_unit_arrays ua, ns_counters *cnt, int q_begin, int lean_i)
+{
+    ns_gate_body<0>(src, prm, u0, n_units, ua, cnt, q_begin, lean_i != 0);
+}
+__global__ void __launch_bounds__(NS_WPB_GATE * 32, 4)
+k_gate_v4(ns_unit_src src, ns_params prm, int64_t u0, int n_units, ns_unit_arrays ua, ns_counters *cnt, int q_begin, int lean_i)
+{
+    ns_gate_body<4>(src, prm, u0, n_units, ua, cnt, q_begin, lean_i != 0);
+}
+__global__ void __launch_bounds__(NS_WPB_GATE * 32, 4)
+k_gate_v2(ns_unit_src src, ns_params prm, int64_t u0, int n_units, ns_unit_arrays ua, ns_counters *cnt, int q_begin, int lean_i)
+{
+    ns_gate_body<2>(src, prm, u0, n_units, ua, cnt, q_begin, lean_i != 0);
 }
 
 __global__ void k_scan_total(const int *flag, const int *excl, int n, int *total)

@@ -59,6 +59,22 @@ struct ns_unit_arrays {
 
 __global__ void k_gate(ns_unit_src src, ns_params prm, int64_t u0, int n_units, ns_unit_arrays ua, ns_counters *cnt, int q_begin,
                        int lean);
+__global__ void k_gate_v4(ns_unit_src src, ns_params prm, int64_t u0, int n_units, ns_unit_arrays ua, ns_counters *cnt, int q_begin,
+                          int lean);
+__global__ void k_gate_v2(ns_unit_src src, ns_params prm, int64_t u0, int n_units, ns_unit_arrays ua, ns_counters *cnt, int q_begin,
+                          int lean);
+/* load form of the streaming gate for SNV planes at `counts` (host and device agree on it): 4, 2 or 0 */
+static inline int ns_gate_form(int mode, int extra_rob, int64_t u0, int n, double min_coverage, const void *counts_at_u0)
+{
+    if (mode != 0 || extra_rob || (u0 % 3) != 0 || !(min_coverage < 2.0e9))
+        return 0;
+    const uintptr_t addr = (uintptr_t)counts_at_u0;
+    if ((n & 3) == 0 && n > 32 && n <= 128 && (addr & 15) == 0)
+        return 4;
+    if ((n & 1) == 0 && n > 16 && n <= 64 && (addr & 7) == 0)
+        return 2;
+    return 0;
+}
 __global__ void k_gate_staged(ns_unit_src src, ns_params prm, int64_t u0, int n_units, ns_unit_arrays ua, ns_counters *cnt,
                               int stage_k, int stages, int n_full_blocks, int lean);
 __global__ void k_fit(ns_unit_src src, const __grid_constant__ ns_params prm, int64_t u0, ns_unit_arrays ua, ns_counters *cnt);

@@ -177,7 +177,8 @@ def compare(O, R, units=None, tol=TOL, gq_thr=50.0, label=""):
             po, pr = np.asarray(O["pvalue"][u], dtype=float), np.asarray(R["pvalue"][u], dtype=float)
             m = np.isfinite(po) & (po > 0) & np.isfinite(pr)
             if m.any():
-                rp = float(np.max(np.abs(pr[m] - po[m]) / po[m]))
+                # (below 2.2e-308 a double is denormal: its last bit alone is 1e-4 of a value of 1e-320)
+                rp = float(np.max(np.maximum(np.abs(pr[m] - po[m]) - 2 * 4.94e-324, 0.0) / po[m]))
                 if utol == tol:
                     rep["max_rel_p"] = max(rep["max_rel_p"], rp)
                 if rp > P_REL_FACTOR * utol:

@@ -140,7 +140,9 @@ def test_driver_with_pairs_file_matches_oracle_fed_formatter(tmp_path, oracle, m
             n_diff += 1
             # (1e-9 absolute: -10 log10 of a Fisher p-value that equals 1 up to rounding prints as +-1e-15 with scipen = 100)
             assert abs(float(a) - float(b)) <= 2e-6 * abs(float(b)) + 1e-9, (a, b)
-    assert n_diff <= 0.005 * n_num, (n_diff, n_num)
+    # sigma is only defined to the 1e-8 (absolute) of the reference's Brent search: relative differences of ~1e-9 in the
+    # printed values straddle a 7-digit rounding boundary about once in a hundred numbers
+    assert n_diff <= 0.02 * n_num, (n_diff, n_num)
     # the statuses and warnings the case was built for are all there
     assert {"SOMATIC", "GERMLINE_CONFIRMED", "POSSIBLE_CONTAMINATION", "UNKNOWN", "GERMLINE_UNCONFIRMABLE", "."} <= seen_status
     contam = [f for g in got for f in g.split("\t")[9:] if "POSSIBLE_CONTAMINATION_FROM_" in f]
