@@ -51,6 +51,8 @@ def parse():
     ap.add_argument("--no-text", action="store_true", help="skip the text-table leg (loader and drop-in driver timings)")
     ap.add_argument("--p-germline", type=float, default=1e-4)
     ap.add_argument("--dump-cycles", default="")
+    ap.add_argument("--gpus-list", default="", help="--scaling strong: comma-separated device counts to run on the SAME "
+                    "host batch, one JSON line each (e.g. 1,2,4,8); default: --gpus only")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="weak: every rank its own region (torchrun, one process per GPU); strong: ONE workload over "
                          "--gpus devices from ONE host process (ns_multi_call_snv), run without torchrun")
@@ -311,14 +313,26 @@ def strong_main(a, cfg, P, n, config, torch, ns):
     torch.cuda.synchronize()
     torch.cuda.empty_cache()
     prm = ns.make_params()
-    m = ns.MultiCaller(list(range(a.gpus)), reuse_outputs=True)
+    counts_list = [int(x) for x in a.gpus_list.split(",") if x] or [a.gpus]
+    base_ms = None
+    for ng in counts_list:
+        line = strong_one(a, cfg, P, n, dict(config), ns, prm, h_ref, h_counts, ng)
+        if base_ms is None:
+            base_ms = (ng, line["ms_per_step"])
+        line["speedup_vs_first"] = {"n_gpus_first": base_ms[0], "speedup": base_ms[1] / line["ms_per_step"]}
+        print(json.dumps(line), flush=True)
+    return 0
+
+
+def strong_one(a, cfg, P, n, config, ns, prm, h_ref, h_counts, ng):
+    m = ns.MultiCaller(list(range(ng)), reuse_outputs=True)
     for _ in range(max(a.warmup, 1)):
         R = m.call_snv(h_ref.array, h_counts.array, prm=prm)
-    samplers = [ClockSampler(i) for i in range(a.gpus)]
+    samplers = [ClockSampler(i) for i in range(ng)]
     for sp in samplers:
         sp.start()
     fitted = 0
-    per_dev = [dict(chunks=0, wall_ms=0.0, device_ms=0.0, gate_ms=0.0, fit_ms=0.0, pool_tail_ms=0.0) for _ in range(a.gpus)]
+    per_dev = [dict(chunks=0, wall_ms=0.0, device_ms=0.0, gate_ms=0.0, fit_ms=0.0, pool_tail_ms=0.0) for _ in range(ng)]
     launches = 0
     t0 = time.perf_counter()
     for _ in range(a.steps):
@@ -341,14 +355,16 @@ def strong_main(a, cfg, P, n, config, torch, ns):
     d2h = U * (8 + 8 + 8 + 4 + 4 + 4) + R.n_emitted * (n * 58 + 8 * 8 + 8)
     value = fitted / (ms * 1e-3)
     # single-context result of the same call: the gather must not change anything
-    with ns.Caller(0) as c1:
-        R1 = c1.call_snv(h_ref.array, h_counts.array, prm=prm)
-    same = bool(R1.n_emitted == R.n_emitted and R1.n_fitted == R.n_fitted and np.array_equal(R1.emit_unit, R.emit_unit)
-                and np.array_equal(R1.gq, R.gq, equal_nan=True) and np.array_equal(R1.sigma, R.sigma, equal_nan=True))
-    config = dict(config, parallelism=f"one host process, {a.gpus} devices, queue of position chunks (ns_multi_call_snv)",
+    same = None
+    if ng > 1:
+        with ns.Caller(0) as c1:
+            R1 = c1.call_snv(h_ref.array, h_counts.array, prm=prm)
+        same = bool(R1.n_emitted == R.n_emitted and R1.n_fitted == R.n_fitted and np.array_equal(R1.emit_unit, R.emit_unit)
+                    and np.array_equal(R1.gq, R.gq, equal_nan=True) and np.array_equal(R1.sigma, R.sigma, equal_nan=True))
+    config = dict(config, parallelism=f"one host process, {ng} devices, queue of position chunks (ns_multi_call_snv)",
                   positions_total=P)
     config.pop("positions_per_gpu", None)
-    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": ng, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic", "config": config,
             "clocks": {"sm_mhz": min((c["sm_mhz"] or 0) for c in clocks), "sm_max_mhz": max((c["sm_max_mhz"] or 0) for c in clocks),
@@ -362,9 +378,8 @@ def strong_main(a, cfg, P, n, config, torch, ns):
             "detail": {"fitted_per_step": R.n_fitted, "emitted_per_step": R.n_emitted,
                        "identical_to_single_device_call": same,
                        "site_alleles_processed_per_s": U * a.steps / (ms * 1e-3)}}
-    print(json.dumps(line))
     m.close()
-    return 0
+    return line
 
 
 def main():
@@ -528,25 +543,32 @@ def main():
     gate_s = tm_sum["gate_ms"] * 1e-3
     gate_bytes = a.steps * (P * (36.0 * n + 1) + 3 * P * 44.0)
     gate_ach = gate_bytes / gate_s / 1e9 if gate_s > 0 else 0.0
-    # DRAM bytes per launch from the committed ncu capture of this same workload (profiles/capture.sh step 3)
+    # DRAM bytes per launch: NOT measured in this run (that needs ncu) - read from the committed ncu capture of this same
+    # workload (profiles/capture.sh step 3) and labelled as such
     traffic = {}
+    traffic_src = None
     if a.config == "C2" and P == cfg.P and n == cfg.n:
         try:
-            tj = sorted(f for f in os.listdir(os.path.join(ROOT, "profiles")) if f.startswith("traffic_r"))[-1]
+            tj = sorted((f for f in os.listdir(os.path.join(ROOT, "profiles")) if f.startswith("traffic_r")),
+                        key=lambda f: os.path.getmtime(os.path.join(ROOT, "profiles", f)))[-1]
             for k, v in json.load(open(os.path.join(ROOT, "profiles", tj)))["kernels"].items():
                 traffic[k] = v["dram_bytes_per_launch"]
+            traffic["k_gate"] = traffic.get("k_gate_v4", traffic.get("k_gate"))
+            traffic_src = f"committed ncu capture profiles/{tj} (same command, earlier run), not this run"
         except Exception:
             traffic = {}
     roofline = {"kernel": "k_fit", "bound": "fp64", "achieved": ach, "peak": fp64_peak, "unit": "TFLOP/s",
-                "frac": ach / fp64_peak if fp64_peak else None, "traffic": traffic.get("k_fit"),
+                "frac": ach / fp64_peak if fp64_peak else None, "traffic": traffic.get("k_fit"), "traffic_source": traffic_src,
+                "peak_datasheet": 37.2, "peak_vs_datasheet": fp64_peak / 37.2 if fp64_peak else None,
                 "peak_source": "DFMA micro-benchmark run in this process (MEASURED_PEAKS.json has no FP64 entry)",
                 "flops_model": "400*N_seed + 32*N_lattice (+ 2000*N_quad, zero in this kernel) (SURVEY.md 8d); "
                                "counters from the kernel",
                 "n_seed": fseeds, "n_lattice": flattice, "all_kernels": {"n_seed": seeds, "n_lattice": lattice,
                                                                        "n_quad": quad},
                 "share_of_step": tm_sum["fit_ms"] / ms if ms else None}
-    roofline_gate = {"kernel": "k_gate", "bound": "hbm", "achieved": gate_ach, "peak": hbm_peak, "unit": "GB/s",
-                     "frac": gate_ach / hbm_peak, "traffic": traffic.get("k_gate"), "peak_source": hbm_src,
+    roofline_gate = {"kernel": "k_gate_v4 / k_gate_v2 / k_gate (by sample count)", "bound": "hbm", "achieved": gate_ach, "peak": hbm_peak, "unit": "GB/s",
+                     "frac": gate_ach / hbm_peak, "traffic": traffic.get("k_gate"), "traffic_source": traffic_src,
+                     "peak_source": hbm_src,
                      "algorithmic_bytes_per_launch": gate_bytes / (a.steps * -(-P // 262144)),
                      "launches_per_step": -(-P // 262144),
                      "bytes_model": "36*n+1 B read per position + 44 B written per unit",

@@ -68,7 +68,7 @@ def load_library():
     L.ns_multi_call_snv_u16.argtypes = [vp, C.POINTER(NsParams), C.c_int, C.c_int64, vp, vp, C.POINTER(NsOut)]
     L.ns_multi_get_timings.argtypes = [vp, C.c_int, C.POINTER(NsTimings), c_dp]
     L.ns_table_parse.restype = vp
-    L.ns_table_parse.argtypes = [C.c_char_p, C.c_size_t, C.c_int, C.c_int, C.c_int, C.c_char_p, C.c_size_t]
+    L.ns_table_parse.argtypes = [C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_int, C.c_char_p, C.c_size_t]
     L.ns_table_free.argtypes = [vp]
     L.ns_table_positions.restype = C.c_int64
     L.ns_table_indel_units.restype = C.c_int64

@@ -50,9 +50,10 @@ def build(force=False, verbose=False):
     if failed:
         raise RuntimeError("nvcc failed building libns_b200.so")
     tmp = LIB + ".tmp"
-    # CUDA runtime: linked statically by default (nvcc's default; the library then has no run-time dependency on a
-    # libcudart.so of the right version).  NS_CUDART=shared links libcudart.so instead (found through the rpath below).
-    cudart = ["-cudart", "shared", "-Xlinker", "-rpath=/usr/local/cuda/lib64"] if os.environ.get("NS_CUDART") == "shared" else []
+    # CUDA runtime: the shared libcudart.so.12 (found through the rpath below, or the copy a loaded torch brings along:
+    # checked on the GPU box, gpurun_out/r2c_cudart_shared.log), so that the shipped library carries only its own code;
+    # NS_CUDART=static restores nvcc's default of linking the runtime in.
+    cudart = [] if os.environ.get("NS_CUDART") == "static" else ["-cudart", "shared", "-Xlinker", "-rpath=/usr/local/cuda/lib64"]
     r = subprocess.run([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", tmp] + cudart + objs,
                        capture_output=True, text=True)
     if r.returncode != 0:

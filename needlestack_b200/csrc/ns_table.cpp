@@ -55,31 +55,40 @@ struct ns_table {
 
 namespace {
 
-/* One cached page-locked buffer: the driver parses chunk after chunk of the same size, and cudaMallocHost /
- * cudaFreeHost of a gigabyte each cost more than parsing it (the loader ran at 1.3 GB/s end to end against 1.9 GB/s
- * for the parse alone).  A released buffer is kept for the next table that fits; a larger request replaces it. */
+/* A small pool of page-locked buffers: the driver parses block after block of the same size with up to three tables
+ * alive at a time (one being parsed, one queued, one on the GPU), and cudaMallocHost / cudaFreeHost of a gigabyte each
+ * cost ten times more than parsing it (0.4 s against 0.04 s for 0.7 GB).  A released buffer is kept for the next table
+ * it fits; the smallest buffer that fits is handed out; beyond NS_PIN_POOL buffers the smallest is dropped. */
+#define NS_PIN_POOL 4
 std::mutex g_pool_mu;
-void *g_pool_ptr = nullptr;
-size_t g_pool_cap = 0;
+void *g_pool_ptr[NS_PIN_POOL] = {nullptr, nullptr, nullptr, nullptr};
+size_t g_pool_cap[NS_PIN_POOL] = {0, 0, 0, 0};
 
 void *pinned_acquire(size_t bytes, size_t &cap)
 {
     {
         std::lock_guard<std::mutex> lk(g_pool_mu);
-        if (g_pool_ptr && g_pool_cap >= bytes && g_pool_cap <= 2 * bytes + (64u << 20)) {
-            void *p = g_pool_ptr;
-            cap = g_pool_cap;
-            g_pool_ptr = nullptr;
-            g_pool_cap = 0;
+        int best = -1;
+        for (int i = 0; i < NS_PIN_POOL; i++)
+            if (g_pool_ptr[i] && g_pool_cap[i] >= bytes && g_pool_cap[i] <= 2 * bytes + (64u << 20) &&
+                (best < 0 || g_pool_cap[i] < g_pool_cap[best]))
+                best = i;
+        if (best >= 0) {
+            void *p = g_pool_ptr[best];
+            cap = g_pool_cap[best];
+            g_pool_ptr[best] = nullptr;
+            g_pool_cap[best] = 0;
             return p;
         }
     }
     void *p = nullptr;
-    if (cudaMallocHost(&p, bytes) != cudaSuccess) {
+    /* a little slack, so that blocks cut at line ends (sizes differ by a few lines) reuse one another's buffers */
+    const size_t want = bytes + bytes / 16 + (1u << 20);
+    if (cudaHostAlloc(&p, want, cudaHostAllocPortable) != cudaSuccess) {
         cudaGetLastError();
         return nullptr;
     }
-    cap = bytes;
+    cap = want;
     return p;
 }
 
@@ -88,10 +97,22 @@ void pinned_release(void *p, size_t cap)
     void *drop = nullptr;
     {
         std::lock_guard<std::mutex> lk(g_pool_mu);
-        if (!g_pool_ptr || g_pool_cap < cap) {
-            drop = g_pool_ptr;
-            g_pool_ptr = p;
-            g_pool_cap = cap;
+        int slot = -1, smallest = 0;
+        for (int i = 0; i < NS_PIN_POOL; i++) {
+            if (!g_pool_ptr[i]) {
+                slot = i;
+                break;
+            }
+            if (g_pool_cap[i] < g_pool_cap[smallest])
+                smallest = i;
+        }
+        if (slot >= 0) {
+            g_pool_ptr[slot] = p;
+            g_pool_cap[slot] = cap;
+        } else if (g_pool_cap[smallest] < cap) {
+            drop = g_pool_ptr[smallest];
+            g_pool_ptr[smallest] = p;
+            g_pool_cap[smallest] = cap;
         } else {
             drop = p;
         }

@@ -399,9 +399,43 @@ def main(argv=None, stdin=None):
     q = queue.Queue(maxsize=1)
     wq = queue.Queue(maxsize=2)
 
+    def whole_input():
+        """the rest of the input as ONE uint8 view when it is addressable without reading it: a regular file on STDIN
+        (`< table`, mmap-ed) or an in-memory buffer; None for a pipe"""
+        try:
+            if hasattr(src, "getbuffer"):
+                return np.frombuffer(src.getbuffer(), dtype=np.uint8)[src.tell():]
+            import mmap
+            import stat
+            fd = src.fileno()
+            st = os.fstat(fd)
+            if stat.S_ISREG(st.st_mode) and st.st_size > 0:
+                mm = mmap.mmap(fd, 0, access=mmap.ACCESS_READ)
+                return np.frombuffer(mm, dtype=np.uint8)[src.tell():]
+        except Exception:
+            pass
+        return None
+
     def blocks():
         """whole-line blocks of the table: --chunk_lines lines each (the reference reads line by line; a line count
-        makes the block boundaries independent of the text), else ~--chunk_bytes bytes read in one call"""
+        makes the block boundaries independent of the text), else ~--chunk_bytes bytes: views into the input when it is
+        a file or a buffer (parsed in place), read() calls when it is a pipe"""
+        whole = whole_input() if o["chunk"] <= 0 else None
+        if whole is not None:
+            pos, end = 0, len(whole)
+            while pos < end:
+                cut = min(pos + o["chunk_bytes"], end)
+                if cut < end:
+                    back = max(pos, cut - (4 << 20))
+                    nl = np.flatnonzero(whole[back:cut] == 10)
+                    if len(nl):
+                        cut = back + int(nl[-1]) + 1
+                    else:  # a line longer than 4 MB: extend to its end
+                        nxt = np.flatnonzero(whole[cut:] == 10)
+                        cut = cut + int(nxt[0]) + 1 if len(nxt) else end
+                yield whole[pos:cut]
+                pos = cut
+            return
         if o["chunk"] > 0:
             while True:
                 lines = []

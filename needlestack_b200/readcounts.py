@@ -72,17 +72,24 @@ class Table:
 
 
 def load_table(source, n_samples, has_header=True, n_threads=None):
-    """source: path, bytes or str holding the whole table"""
-    if isinstance(source, (bytes, bytearray)):
-        data = bytes(source)
-    elif isinstance(source, str) and ("\t" in source or "\n" in source):
-        data = source.encode()
+    """source: path, bytes or str holding the whole table, or a uint8 numpy array over its text (parsed in place: a
+    view into an mmap-ed file or a BytesIO buffer, no copy)"""
+    keep = None
+    if isinstance(source, np.ndarray):
+        keep = np.ascontiguousarray(source, dtype=np.uint8)
+        data, size = C.c_void_p(keep.ctypes.data), keep.size
     else:
-        with open(source, "rb") as f:
-            data = f.read()
+        if isinstance(source, (bytes, bytearray)):
+            data = bytes(source)
+        elif isinstance(source, str) and ("\t" in source or "\n" in source):
+            data = source.encode()
+        else:
+            with open(source, "rb") as f:
+                data = f.read()
+        size = len(data)
     L = api.load_library()
     err = C.create_string_buffer(512)
-    h = L.ns_table_parse(data, len(data), int(n_samples), int(bool(has_header)),
+    h = L.ns_table_parse(data, size, int(n_samples), int(bool(has_header)),
                          int(n_threads or os.cpu_count() or 1), err, 512)
     if not h:
         raise api.NeedlestackError(err.value.decode() or "ns_table_parse failed")

@@ -13,10 +13,10 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-fil
     python bench.py --steps 2 --warmup 1 --no-cpu > $O/ncu_launch_${TAG}.log 2>&1
 # 3. DRAM traffic of the two roofline kernels inside the bench workload (per launch = per chunk of 262144 positions)
 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none \
-    -k 'regex:^k_(fit|gate)$' -c 16 --csv --log-file $O/traffic_${TAG}.csv \
+    -k 'regex:^k_(fit|gate|gate_v4|gate_v2)$' -c 16 --csv --log-file $O/traffic_${TAG}.csv \
     python bench.py --steps 2 --warmup 1 --no-cpu --no-e2e > $O/ncu_traffic_${TAG}.log 2>&1
 # 4. full-set captures of our kernels on the fixed small case
 python profiles/profile_case.py 60000 1e-4 > $O/prof_${TAG}_plain.log 2>&1 || exit 1
-ncu --set full --clock-control none --import-source on -k 'regex:^k_(fit|gate|post|fit_heavy|pack)$' -c 5 -f \
+ncu --set full --clock-control none --import-source on -k 'regex:^k_(fit|gate|gate_v4|gate_v2|post|fit_heavy|pack)$' -c 5 -f \
     -o $O/prof_${TAG}_full python profiles/profile_case.py 60000 1e-4 > $O/ncu_full_${TAG}.log 2>&1
 tail -c 400 $O/bench_${TAG}_full.json; echo; tail -2 $O/ncu_full_${TAG}.log

@@ -9,7 +9,7 @@ import sys
 
 TAG = sys.argv[1] if len(sys.argv) > 1 else "r1"
 SRC, DST = "gpurun_out", "profiles"
-OURS = ("k_gate", "k_fit_heavy_tp", "k_fit_heavy", "k_fit", "k_post", "k_pack", "k_qtab", "k_dfma", "k_scan_total", "k_qgrid", "DeviceScan")
+OURS = ("k_gate_staged", "k_gate_v4", "k_gate_v2", "k_gate", "k_pool_gather", "k_widen16", "k_fit_heavy_tp", "k_fit_heavy", "k_fit", "k_post", "k_pack", "k_qtab", "k_dfma", "k_scan_total", "k_qgrid", "DeviceScan")
 
 
 def short(name):

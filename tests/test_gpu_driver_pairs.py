@@ -146,7 +146,8 @@ def test_driver_with_pairs_file_matches_oracle_fed_formatter(tmp_path, oracle, m
     # the statuses and warnings the case was built for are all there
     assert {"SOMATIC", "GERMLINE_CONFIRMED", "POSSIBLE_CONTAMINATION", "UNKNOWN", "GERMLINE_UNCONFIRMABLE", "."} <= seen_status
     contam = [f for g in got for f in g.split("\t")[9:] if "POSSIBLE_CONTAMINATION_FROM_" in f]
-    assert contam and all(f.rstrip("\n").split("FROM_")[1].startswith("P02T_P22N") for f in contam[:3])
+    # ... FROM_<every sample with a GERMLINE* / UNKNOWN status>, in sample order: the confirmed pair is always there
+    assert contam and all({"P02T", "P22N"} <= set(f.rstrip("\n").split("FROM_")[1].split("_")) for f in contam)
     assert "WARN=INV_REF" in seen_warn
     if extra_rob:
         assert {"WARN=EXTRA_ROBUST_GL", "WARN=EXTRA_ROBUST_GL/INV_REF"} <= seen_warn
