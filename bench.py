@@ -229,6 +229,8 @@ def text_leg(cfg, device, positions=16000, tile=12):
         raw = open("t.tsv", "rb").read()
         nl = raw.index(b"\n") + 1
         text = raw[:nl] + raw[nl:] * tile
+        with open("tiled.tsv", "wb") as f:  # the driver reads a FILE on its STDIN (mmap-ed, parsed in place)
+            f.write(text)
         P = positions * tile
         best = None
         for _ in range(3):
@@ -240,9 +242,10 @@ def text_leg(cfg, device, positions=16000, tile=12):
         runs = []
         nrec = 0
         for _ in range(3):
-            t = time.perf_counter()
-            driver.main(["--out_file=out.vcf", f"--device={device}"], stdin=io.BytesIO(text))
-            runs.append(time.perf_counter() - t)
+            with open("tiled.tsv", "rb") as f:
+                t = time.perf_counter()
+                driver.main(["--out_file=out.vcf", f"--device={device}"], stdin=f)
+                runs.append(time.perf_counter() - t)
         with open("out.vcf", "rb") as f:
             nrec = sum(1 for ln in f if not ln.startswith(b"#"))
         dt = min(runs[1:])
@@ -250,7 +253,8 @@ def text_leg(cfg, device, positions=16000, tile=12):
                          f"{len(text) / 1e9:.2f} GB", "loader_gbs": len(text) / 1e9 / best, "loader_s": best,
                 "loader_threads": os.cpu_count(), "driver_s": dt, "driver_gbs": len(text) / 1e9 / dt,
                 "driver_site_alleles_per_s": 3 * P / dt, "vcf_records": nrec,
-                "driver": "python -m needlestack_b200.driver (block reader, C++ loader, ns_call_snv, C++ VCF writer)"}
+                "driver": "python -m needlestack_b200.driver < table (mmap-ed input parsed in place, C++ loader, ns_call_snv, "
+                          "C++ VCF writer; reader / GPU / writer stages overlapped)"}
     finally:
         os.chdir(cwd)
         import shutil

@@ -1025,16 +1025,22 @@ static int ns_run_chunk(ns_ctx *ctx, const ns_params &dprm, const double *qtab, 
             ctx->err = "too many samples for the on-chip working set (n > ~1100)";
             return NS_ERR_ARG;
         }
-        CK(ns_need_smem(ctx, 4, k_fit, sm));
+        /* samples per lane in flight: 4 (k_fit4) for panels of more than 64 samples, else 2 (k_fit) */
+        int chains = n > 64 ? 4 : 2;
+        const char *ech = getenv("NS_FIT_CHAINS");
+        if (ech && (atoi(ech) == 2 || atoi(ech) == 4))
+            chains = atoi(ech);
+        auto kfit = chains == 4 ? k_fit4 : k_fit;
+        CK(ns_need_smem(ctx, chains == 4 ? 7 : 4, kfit, sm));
         int bps = 0;
-        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_fit, wpb * 32, sm));
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kfit, wpb * 32, sm));
         if (bps < 1)
             bps = 1;
         int blocks = ctx->sm_count * bps;
         int need = (n_light + wpb - 1) / wpb;
         if (blocks > need)
             blocks = need;
-        k_fit<<<blocks, wpb * 32, sm, st>>>(src, dprm, u0_src, ua, ctx->counters.p);
+        kfit<<<blocks, wpb * 32, sm, st>>>(src, dprm, u0_src, ua, ctx->counters.p);
         CK(cudaGetLastError());
         ctx->tm.kernel_launches++;
     }
@@ -1209,8 +1215,17 @@ int64_t ns_pick_chunk(ns_ctx *ctx, int n, int64_t total_units)
     c -= c % 3;
     if (c < 3)
         c = 3;
-    if (c > total_units)
-        c = total_units;
+    if (c >= total_units)
+        return total_units;
+    if (ctx->chunk_units <= 0) {
+        /* equal chunks: a short last chunk has too little fit work to hide the critical path of its cluster-path units
+         * (the call then waits tens of ms for them); whole groups of 64 positions keep every chunk start 16-byte aligned */
+        const int64_t n_chunks = (total_units + c - 1) / c;
+        int64_t per = (total_units / 3 + n_chunks - 1) / n_chunks;
+        per = (per + 63) / 64 * 64;
+        if (3 * per < c)
+            c = 3 * per;
+    }
     return c;
 }
 
