@@ -297,8 +297,9 @@ def strong_main(a, cfg, P, n, config, torch, ns):
     memory, ns_multi_call_snv hands chunks of positions to one host thread per device and gathers the rows in
     genomic order.  Every step is a whole call (H2D, kernels, D2H, gather inside the timed region)."""
     nd = torch.cuda.device_count()
-    if a.gpus > nd:
-        raise SystemExit(f"bench.py --scaling strong --gpus {a.gpus}: only {nd} devices visible")
+    want = max([int(x) for x in a.gpus_list.split(",") if x] or [a.gpus])
+    if want > nd:
+        raise SystemExit(f"bench.py --scaling strong: {want} devices asked for, only {nd} visible")
     dev = torch.device("cuda", 0)
     torch.cuda.set_device(0)
     h_counts = ns.PinnedArray((P, 9, n), np.int32)
@@ -320,7 +321,7 @@ def strong_main(a, cfg, P, n, config, torch, ns):
     counts_list = [int(x) for x in a.gpus_list.split(",") if x] or [a.gpus]
     base_ms = None
     for ng in counts_list:
-        line = strong_one(a, cfg, P, n, dict(config), ns, prm, h_ref, h_counts, ng)
+        line = strong_one(a, cfg, P, n, dict(config), ns, prm, h_ref, h_counts, ng, check=(ng == counts_list[-1]))
         if base_ms is None:
             base_ms = (ng, line["ms_per_step"])
         line["speedup_vs_first"] = {"n_gpus_first": base_ms[0], "speedup": base_ms[1] / line["ms_per_step"]}
@@ -328,7 +329,7 @@ def strong_main(a, cfg, P, n, config, torch, ns):
     return 0
 
 
-def strong_one(a, cfg, P, n, config, ns, prm, h_ref, h_counts, ng):
+def strong_one(a, cfg, P, n, config, ns, prm, h_ref, h_counts, ng, check=True):
     m = ns.MultiCaller(list(range(ng)), reuse_outputs=True)
     for _ in range(max(a.warmup, 1)):
         R = m.call_snv(h_ref.array, h_counts.array, prm=prm)
@@ -360,7 +361,7 @@ def strong_one(a, cfg, P, n, config, ns, prm, h_ref, h_counts, ng):
     value = fitted / (ms * 1e-3)
     # single-context result of the same call: the gather must not change anything
     same = None
-    if ng > 1:
+    if ng > 1 and check:
         with ns.Caller(0) as c1:
             R1 = c1.call_snv(h_ref.array, h_counts.array, prm=prm)
         same = bool(R1.n_emitted == R.n_emitted and R1.n_fitted == R.n_fitted and np.array_equal(R1.emit_unit, R.emit_unit)

@@ -686,6 +686,13 @@ static int ns_pool_submit(ns_ctx *ctx, const ns_params &dprm, const ns_unit_src 
     const char *emc = getenv("NS_POOL_MAX_CLUSTERS");
     if (emc && atoi(emc) > 0)
         max_cl = atoi(emc);
+    /* Earlier pool launches still running (streaming shapes: a chunk takes less time than one cluster-path unit): the new
+     * clusters could not become resident whatever the host does, and waiting for them would only stall the chunk */
+    if (wait_resident)
+        for (int i = 0; i < NS_POOL_STREAMS; i++)
+            if (pl.used[i] && pl.n_launch > 0 && cudaEventQuery(pl.ev_t1[i]) == cudaErrorNotReady)
+                wait_resident = false;
+    cudaGetLastError();
     int *started = wait_resident ? ctx->d_started : nullptr;
     if (wait_resident)
         *(volatile int *)ctx->h_started = 0;
@@ -699,7 +706,7 @@ static int ns_pool_submit(ns_ctx *ctx, const ns_params &dprm, const ns_unit_src 
          * wait on a mapped flag until the clusters are resident (not a kernel waiting on a kernel) */
         const auto t0 = std::chrono::steady_clock::now();
         while (*(volatile int *)ctx->h_started < ncl) {
-            if (std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() > 0.02)
+            if (std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() > 0.005)
                 break;
         }
     }
@@ -1025,22 +1032,18 @@ static int ns_run_chunk(ns_ctx *ctx, const ns_params &dprm, const double *qtab, 
             ctx->err = "too many samples for the on-chip working set (n > ~1100)";
             return NS_ERR_ARG;
         }
-        /* samples per lane in flight: 4 (k_fit4) for panels of more than 64 samples, else 2 (k_fit) */
-        int chains = n > 64 ? 4 : 2;
-        const char *ech = getenv("NS_FIT_CHAINS");
-        if (ech && (atoi(ech) == 2 || atoi(ech) == 4))
-            chains = atoi(ech);
-        auto kfit = chains == 4 ? k_fit4 : k_fit;
-        CK(ns_need_smem(ctx, chains == 4 ? 7 : 4, kfit, sm));
+        /* (four samples per lane in flight at 128 registers / 16 warps per SM was measured and dropped: C2 441 ms per
+         * step against 353 ms for two samples per lane at 96 registers / 20 warps; profiles/README.md, round 2) */
+        CK(ns_need_smem(ctx, 4, k_fit, sm));
         int bps = 0;
-        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kfit, wpb * 32, sm));
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_fit, wpb * 32, sm));
         if (bps < 1)
             bps = 1;
         int blocks = ctx->sm_count * bps;
         int need = (n_light + wpb - 1) / wpb;
         if (blocks > need)
             blocks = need;
-        kfit<<<blocks, wpb * 32, sm, st>>>(src, dprm, u0_src, ua, ctx->counters.p);
+        k_fit<<<blocks, wpb * 32, sm, st>>>(src, dprm, u0_src, ua, ctx->counters.p);
         CK(cudaGetLastError());
         ctx->tm.kernel_launches++;
     }

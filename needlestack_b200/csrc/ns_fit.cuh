@@ -449,7 +449,7 @@ struct ns_deflist {
 
 /* out of line on purpose: three call sites in the Brent driver; inlining them tripled the kernel's
  * code and the warps stalled on instruction fetch (ncu: 32 % of issue stalls) */
-template <class G, int MODE, int NCH = 2>
+template <class G, int MODE>
 NS_GFN double ns_sig_objective(double sig, const ns_work &w, int n, const ns_params &prm, ns_fit_counters &cnt,
                                      int &need_heavy)
 {
@@ -458,9 +458,6 @@ NS_GFN double ns_sig_objective(double sig, const ns_work &w, int n, const ns_par
     double acc = 0;
     int qerr = 0;
     if (MODE == 1) {
-        /* NCH samples per lane in flight (independent chains through the seed and one joint window loop): 2 in the
-         * 96-register kernel, 4 in the 128-register kernel for panels of more than 64 samples - the warps wait on
-         * fixed-latency FP64 dependencies, and the chains in flight per scheduler are what hides them */
         G::fill_dtab(w.dtab, w.r2tab, w.rtab, invsig, NS_JTAB);
         double dg0 = 0;
         int have_dg0 = 0;
@@ -469,76 +466,63 @@ NS_GFN double ns_sig_objective(double sig, const ns_work &w, int n, const ns_par
         const ns_sptr s_x(w.x), s_mu(w.mu), s_y(w.y), s_dtab(w.dtab), s_r2(w.r2tab);
         unsigned n_seed = 0, n_lat = 0; /* kept in registers, added to cnt once */
         const int nl = G::nl();
-        double accs[NCH];
-#pragma unroll
-        for (int k = 0; k < NCH; k++)
-            accs[k] = 0;
-        for (int i0 = G::lane(); i0 < n; i0 += NCH * nl) {
-            ns_fseed S[NCH];
-            double lg[NCH], imp[NCH], q[NCH], D[NCH], pm[NCH], a[NCH], ty[NCH];
-            int yi[NCH];
-            bool v[NCH];
-            int Jm = -1;
-#pragma unroll
-            for (int k = 0; k < NCH; k++) {
-                const int i = i0 + k * nl;
-                const int ic = i < n ? i : i0;
-                v[k] = (i < n) && (s_x[ic] > 0);
-                S[k].mu = v[k] ? s_mu[ic] : 1.0;
-                S[k].y = v[k] ? s_y[ic] : 0.0;
-            }
-#pragma unroll
-            for (int k = 0; k < NCH; k++)
-                ns_fast_seed(S[k], v[k], sig, invsig, c, inv_c, w.ltab, lg[k]);
+        double accB = 0;
+        for (int iA = G::lane(); iA < n; iA += 2 * nl) {
+            const int iB = (iA + nl < n) ? iA + nl : iA;
+            const bool vA = s_x[iA] > 0, vB = (iB != iA) && (s_x[iB] > 0);
+            ns_fseed A, B;
+            A.mu = vA ? s_mu[iA] : 1.0;
+            A.y = vA ? s_y[iA] : 0.0;
+            B.mu = vB ? s_mu[iB] : 1.0;
+            B.y = vB ? s_y[iB] : 0.0;
+            double lgA, lgB;
+            ns_fast_seed(A, vA, sig, invsig, c, inv_c, w.ltab, lgA);
+            ns_fast_seed(B, vB, sig, invsig, c, inv_c, w.ltab, lgB);
             /* window {0..J2}: everything by recurrence, no division inside the loop.
              * t_j = (j-mu)/(c sd) = t0 + j/(c sd);  psi_j = D_j - lg - (j-mu)/(mu+1/sig) = D_j + C0 - j/(mu+1/sig),
              * 1/(mu+1/sig) = sig/(1+sig mu) = sig mu / V */
-#pragma unroll
-            for (int k = 0; k < NCH; k++) {
-                imp[k] = (sig * S[k].mu) * (S[k].isd * S[k].isd);
-                q[k] = S[k].mu * imp[k];
-                /* a y beyond the window meets weight 0 (or no lattice point at all): tukeypsi(r) = 0 there */
-                yi[k] = (S[k].y < (double)NS_JTAB) ? (int)S[k].y : NS_JTAB;
-                D[k] = q[k] - lg[k]; /* D = digamma(j+1/sig) - digamma(1/sig) + C0 */
-                pm[k] = S[k].pm;
-                a[k] = 0;
-                ty[k] = 0;
-                Jm = S[k].J2 > Jm ? S[k].J2 : Jm;
-            }
-            double jd = 0.0;
+            const double impA = (sig * A.mu) * (A.isd * A.isd), impB = (sig * B.mu) * (B.isd * B.isd);
+            const double qA = A.mu * impA, qB = B.mu * impB;
+            /* a y beyond the window meets weight 0 (or no lattice point at all): tukeypsi(r) = 0 there */
+            const int yiA = (A.y < (double)NS_JTAB) ? (int)A.y : NS_JTAB, yiB = (B.y < (double)NS_JTAB) ? (int)B.y : NS_JTAB;
+            double DA = qA - lgA, DB = qB - lgB; /* D = digamma(j+1/sig) - digamma(1/sig) + C0 */
+            double pmA = A.pm, pmB = B.pm, aA = 0, aB = 0, tyA = 0, tyB = 0, jd = 0.0;
+            const int Jm = A.J2 > B.J2 ? A.J2 : B.J2;
             NS_UNROLL1
             for (int j = 0; j <= Jm; j++) {
                 const double r2 = s_r2[j], dt = s_dtab[j];
-#pragma unroll
-                for (int k = 0; k < NCH; k++) {
-                    const double t = fma(jd, S[k].ics, S[k].t0);
-                    const double wt = ns_biweight(fma(t, t, -1.0));
-                    const double wpsi = wt * fma(-jd, imp[k], D[k]);
-                    a[k] = fma(wpsi, pm[k], a[k]);
-                    ty[k] = (j == yi[k]) ? wpsi : ty[k]; /* (psi_c(r)/r) * psi.sig.ML(r) at r = (y-mu)/sd */
-                    pm[k] *= r2 * q[k];
-                    D[k] += dt;
-                }
+                const double tA = fma(jd, A.ics, A.t0), tB = fma(jd, B.ics, B.t0);
+                const double wA = ns_biweight(fma(tA, tA, -1.0)), wB = ns_biweight(fma(tB, tB, -1.0));
+                const double wpsiA = wA * fma(-jd, impA, DA), wpsiB = wB * fma(-jd, impB, DB);
+                aA = fma(wpsiA, pmA, aA);
+                aB = fma(wpsiB, pmB, aB);
+                tyA = (j == yiA) ? wpsiA : tyA; /* (psi_c(r)/r) * psi.sig.ML(r) at r = (y-mu)/sd */
+                tyB = (j == yiB) ? wpsiB : tyB;
+                pmA *= r2 * qA;
+                pmB *= r2 * qB;
+                DA += dt;
+                DB += dt;
                 jd += 1.0;
             }
-#pragma unroll
-            for (int k = 0; k < NCH; k++) {
-                double term = ty[k] - a[k];
-                if (S[k].y == S[k].mu)
-                    term = NAN; /* r == 0: tukeypsi(r)/r = 0/0 in R */
-                if (S[k].J2 < 0)
-                    term = 0; /* no sample here, or one for ns_obj_slow */
-                n_seed += (unsigned)v[k];
-                n_lat += (unsigned)(S[k].J2 + 1);
-                if (S[k].slow)
-                    term = ns_obj_slow(S[k].mu, S[k].y, sig, c, twon, &dg0, &have_dg0, &need_heavy, &n_lat);
-                accs[k] += term;
-            }
+            double termA = tyA - aA, termB = tyB - aB;
+            if (A.y == A.mu)
+                termA = NAN; /* r == 0: tukeypsi(r)/r = 0/0 in R */
+            if (B.y == B.mu)
+                termB = NAN;
+            if (A.J2 < 0)
+                termA = 0; /* no sample here, or one for ns_obj_slow */
+            if (B.J2 < 0)
+                termB = 0;
+            n_seed += (unsigned)vA + (unsigned)vB;
+            n_lat += (unsigned)(A.J2 + 1) + (unsigned)(B.J2 + 1);
+            if (A.slow)
+                termA = ns_obj_slow(A.mu, A.y, sig, c, twon, &dg0, &have_dg0, &need_heavy, &n_lat);
+            if (B.slow)
+                termB = ns_obj_slow(B.mu, B.y, sig, c, twon, &dg0, &have_dg0, &need_heavy, &n_lat);
+            acc += termA;
+            accB += termB;
         }
-        acc = accs[0];
-#pragma unroll
-        for (int k = 1; k < NCH; k++)
-            acc += accs[k];
+        acc += accB;
         cnt.n_seed += n_seed;
         cnt.n_lattice += n_lat;
     } else {
@@ -645,13 +629,13 @@ NS_GFN double ns_sig_objective(double sig, const ns_work &w, int n, const ns_par
 
 /* uniroot(sig.rob.tukey, c(minsig,maxsig), tol=sig.prec, maxiter=maxit.sig)$root: R's
  * end-point checks followed by R_zeroin2 (Brent).  Returns false on any R error. */
-template <class G, int MODE, int NCH = 2>
+template <class G, int MODE>
 NS_GF inline bool ns_sigma_root(const ns_work &w, int n, const ns_params &prm, ns_fit_result &res, double &root,
                                 int &need_heavy)
 {
     double a = prm.minsig, b = prm.maxsig;
-    double fa = ns_sig_objective<G, MODE, NCH>(a, w, n, prm, res.cnt, need_heavy);
-    double fb = ns_sig_objective<G, MODE, NCH>(b, w, n, prm, res.cnt, need_heavy);
+    double fa = ns_sig_objective<G, MODE>(a, w, n, prm, res.cnt, need_heavy);
+    double fb = ns_sig_objective<G, MODE>(b, w, n, prm, res.cnt, need_heavy);
     res.n_obj += 2;
     if (MODE == 1 && G::any(need_heavy))
         return false;
@@ -712,7 +696,7 @@ NS_GF inline bool ns_sigma_root(const ns_work &w, int n, const ns_params &prm, n
         a = b;
         fa = fb;
         b += new_step;
-        fb = ns_sig_objective<G, MODE, NCH>(b, w, n, prm, res.cnt, need_heavy);
+        fb = ns_sig_objective<G, MODE>(b, w, n, prm, res.cnt, need_heavy);
         res.n_obj += 1;
         if (MODE == 1 && G::any(need_heavy))
             return false;
@@ -743,7 +727,7 @@ NS_HD double ns_D_absmax(double u0, int ulen, double v0, int vlen)
 }
 
 /* one IRLS pass (glm_rob_nb.r:188-200): returns the new beta, updates mu/eta */
-template <class G, int MODE, int NCH = 2>
+template <class G, int MODE>
 NS_GFN double ns_irls_step(double sig, const ns_work &w, int n, double maxmu, const ns_params &prm,
                                  ns_fit_result &res, int &need_heavy)
 {
@@ -756,72 +740,72 @@ NS_GFN double ns_irls_step(double sig, const ns_work &w, int n, double maxmu, co
     const ns_sptr s_x(w.x), s_mu(w.mu), s_y(w.y), s_eta(w.eta), s_X(w.X), s_r2(w.r2tab);
     unsigned n_seed = 0, n_lat = 0;
     if (MODE == 1) {
-        /* NCH samples per lane in flight (see ns_sig_objective).  With y1 = 1/sqrt(V): 1/(V sqrt V) = y1^3,
+        /* two samples per lane in flight (see ns_fast_seed).  With y1 = 1/sqrt(V): 1/(V sqrt V) = y1^3,
          * mu/(mu+1/sig) = sig mu^2 y1^2, V/mu = 1 + sig mu */
         const double inv_c = ns_frcp(c);
         const int nl = G::nl();
-        for (int i0 = lane; i0 < n; i0 += NCH * nl) {
-            ns_fseed S[NCH];
-            double lg[NCH], q[NCH], pm[NCH], a1[NCH], a2[NCH];
-            bool v[NCH];
-            int idx[NCH];
-            int Jm = -1;
-#pragma unroll
-            for (int k = 0; k < NCH; k++) {
-                const int i = i0 + k * nl;
-                idx[k] = i < n ? i : i0;
-                v[k] = (i < n) && (s_x[idx[k]] > 0);
-                S[k].mu = v[k] ? s_mu[idx[k]] : 1.0;
-                S[k].y = v[k] ? s_y[idx[k]] : 0.0;
-            }
-#pragma unroll
-            for (int k = 0; k < NCH; k++)
-                ns_fast_seed(S[k], v[k], sig, invsig, c, inv_c, w.ltab, lg[k]);
-#pragma unroll
-            for (int k = 0; k < NCH; k++) {
-                q[k] = (sig * S[k].mu * S[k].mu) * (S[k].isd * S[k].isd);
-                pm[k] = S[k].pm;
-                a1[k] = 0;
-                a2[k] = 0;
-                Jm = S[k].J2 > Jm ? S[k].J2 : Jm;
-            }
-            double jd = 0.0;
+        for (int iA = lane; iA < n; iA += 2 * nl) {
+            const int iB = (iA + nl < n) ? iA + nl : iA;
+            const bool vA = s_x[iA] > 0, vB = (iB != iA) && (s_x[iB] > 0);
+            ns_fseed A, B;
+            A.mu = vA ? s_mu[iA] : 1.0;
+            A.y = vA ? s_y[iA] : 0.0;
+            B.mu = vB ? s_mu[iB] : 1.0;
+            B.y = vB ? s_y[iB] : 0.0;
+            double lgA, lgB;
+            ns_fast_seed(A, vA, sig, invsig, c, inv_c, w.ltab, lgA);
+            ns_fast_seed(B, vB, sig, invsig, c, inv_c, w.ltab, lgB);
+            const double qA = (sig * A.mu * A.mu) * (A.isd * A.isd), qB = (sig * B.mu * B.mu) * (B.isd * B.isd);
+            double pmA = A.pm, pmB = B.pm, a1A = 0, a2A = 0, a1B = 0, a2B = 0, jd = 0.0;
+            const int Jm = A.J2 > B.J2 ? A.J2 : B.J2;
             NS_UNROLL1
             for (int j = 0; j <= Jm; j++) {
                 const double r2 = s_r2[j];
-#pragma unroll
-                for (int k = 0; k < NCH; k++) {
-                    const double t = fma(jd, S[k].ics, S[k].t0);
-                    const double wt = ns_biweight(fma(t, t, -1.0));
-                    const double d = jd - S[k].mu;
-                    const double wpd = (wt * pm[k]) * d;
-                    a1[k] += wpd;
-                    a2[k] = fma(wpd, d, a2[k]);
-                    pm[k] *= r2 * q[k];
-                }
+                const double tA = fma(jd, A.ics, A.t0), tB = fma(jd, B.ics, B.t0);
+                const double wA = ns_biweight(fma(tA, tA, -1.0)), wB = ns_biweight(fma(tB, tB, -1.0));
+                const double dA = jd - A.mu, dB = jd - B.mu;
+                const double wpdA = (wA * pmA) * dA, wpdB = (wB * pmB) * dB;
+                a1A += wpdA;
+                a2A = fma(wpdA, dA, a2A);
+                a1B += wpdB;
+                a2B = fma(wpdB, dB, a2B);
+                pmA *= r2 * qA;
+                pmB *= r2 * qB;
                 jd += 1.0;
             }
-#pragma unroll
-            for (int k = 0; k < NCH; k++) {
-                double e1 = a1[k] * S[k].isd, sap = a2[k] * S[k].isd;
-                n_seed += (unsigned)v[k];
-                n_lat += (unsigned)(S[k].J2 + 1);
-                bool use = v[k];
-                if (S[k].slow && !ns_irls_slow(S[k].mu, sig, c, twon, &e1, &sap, &n_lat)) {
-                    need_heavy = 1;
-                    use = false;
+            double e1A = a1A * A.isd, sapA = a2A * A.isd, e1B = a1B * B.isd, sapB = a2B * B.isd;
+            n_seed += (unsigned)vA + (unsigned)vB;
+            n_lat += (unsigned)(A.J2 + 1) + (unsigned)(B.J2 + 1);
+            bool useA = vA, useB = vB;
+            if (A.slow && !ns_irls_slow(A.mu, sig, c, twon, &e1A, &sapA, &n_lat)) {
+                need_heavy = 1;
+                useA = false;
+            }
+            if (B.slow && !ns_irls_slow(B.mu, sig, c, twon, &e1B, &sapB, &n_lat)) {
+                need_heavy = 1;
+                useB = false;
+            }
+            /* derivinvlink(eta) = exp(log(mu)) = mu */
+            const double biA = sapA * (A.isd * A.isd * A.isd) * (A.mu * A.mu);
+            const double biB = sapB * (B.isd * B.isd * B.isd) * (B.mu * B.mu);
+            const double eiA = (ns_tukeypsi_f((A.y - A.mu) * A.isd, c, inv_c) - e1A) * ns_frcp(sapA) * A.s1;
+            const double eiB = (ns_tukeypsi_f((B.y - B.mu) * B.isd, c, inv_c) - e1B) * ns_frcp(sapB) * B.s1;
+            if (useA) {
+                const double zi = s_eta[iA] + eiA;
+                if (biA != biA || zi != zi) {
+                    nanrows++; /* lm(): na.omit drops the row */
+                } else if (biA != 0) { /* lm.wfit(): zero-weight rows excluded */
+                    sw += biA;
+                    swz += biA * (zi - s_X[iA]);
                 }
-                /* derivinvlink(eta) = exp(log(mu)) = mu */
-                const double bi = sap * (S[k].isd * S[k].isd * S[k].isd) * (S[k].mu * S[k].mu);
-                const double ei = (ns_tukeypsi_f((S[k].y - S[k].mu) * S[k].isd, c, inv_c) - e1) * ns_frcp(sap) * S[k].s1;
-                if (use) {
-                    const double zi = s_eta[idx[k]] + ei;
-                    if (bi != bi || zi != zi) {
-                        nanrows++; /* lm(): na.omit drops the row */
-                    } else if (bi != 0) { /* lm.wfit(): zero-weight rows excluded */
-                        sw += bi;
-                        swz += bi * (zi - s_X[idx[k]]);
-                    }
+            }
+            if (useB) {
+                const double zi = s_eta[iB] + eiB;
+                if (biB != biB || zi != zi) {
+                    nanrows++;
+                } else if (biB != 0) {
+                    sw += biB;
+                    swz += biB * (zi - s_X[iB]);
                 }
             }
         }
@@ -950,7 +934,7 @@ static thread_local int ns_fit_trace_cap = 0;
 /* The fit proper: glm_rob_nb.r:58-205 on the samples with w.x[i] > 0.
  * Expects w.y / w.x filled (x <= 0 for samples outside the fit); maxmu = max(x) over ALL
  * samples of the unit (:20). */
-template <class G, int MODE, int NCH = 2>
+template <class G, int MODE>
 NS_GF inline void ns_fit_unit(const ns_work &w, int n, double maxmu, const ns_params &prm, ns_fit_result &res)
 {
     const int lane = G::llane(); /* the initial estimates are computed by every replica */
@@ -1089,7 +1073,7 @@ NS_GF inline void ns_fit_unit(const ns_work &w, int n, double maxmu, const ns_pa
         len00 = len11;
         /* :175-182 */
         double root = NAN;
-        bool ok = ns_sigma_root<G, MODE, NCH>(w, n, prm, res, root, need_heavy);
+        bool ok = ns_sigma_root<G, MODE>(w, n, prm, res, root, need_heavy);
         if (MODE == 1 && G::any(need_heavy)) {
             res.deferred = 1;
             return;
@@ -1116,7 +1100,7 @@ NS_GF inline void ns_fit_unit(const ns_work &w, int n, double maxmu, const ns_pa
         while (ns_D_absmax(beta1, len1, beta0, len0) > tol && it_mu < prm.maxit) {
             beta0 = beta1;
             len0 = len1;
-            beta1 = ns_irls_step<G, MODE, NCH>(sig, w, n, maxmu, prm, res, need_heavy);
+            beta1 = ns_irls_step<G, MODE>(sig, w, n, maxmu, prm, res, need_heavy);
             len1 = 2;
             if (MODE == 1 && G::any(need_heavy)) {
                 res.deferred = 1;

@@ -68,13 +68,12 @@ __device__ __forceinline__ void ns_store_fit(const ns_unit_arrays &ua, int u, ui
     ua.cycles[u] = (unsigned long long)(clock64() - t_start);
 }
 
-/* persistent warps, one unit per warp at a time, fast (table/recurrence) path; NCH = samples per lane in flight */
+/* persistent warps, one unit per warp at a time, fast (table/recurrence) path */
 #ifndef NS_FIT_MINB
 #define NS_FIT_MINB 5
 #endif
-template <int NCH>
-static __device__ __forceinline__ void ns_fit_body(const ns_unit_src &src, const ns_params &prm, int64_t u0,
-                                                   const ns_unit_arrays &ua, ns_counters *cnt)
+__global__ void __launch_bounds__(128, NS_FIT_MINB)
+k_fit(ns_unit_src src, const __grid_constant__ ns_params prm, int64_t u0, ns_unit_arrays ua, ns_counters *cnt)
 {
     const int n = src.n;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -102,7 +101,7 @@ static __device__ __forceinline__ void ns_fit_body(const ns_unit_src &src, const
         maxmu = WarpG::max(maxmu);
         __syncwarp();
         ns_fit_result res;
-        ns_fit_unit<WarpG, 1, NCH>(w, n, maxmu, prm, res);
+        ns_fit_unit<WarpG, 1>(w, n, maxmu, prm, res);
         if (res.deferred) {
             /* needs the spline + quadrature branch: one CTA per unit in k_fit_heavy */
             if (lane == 0)
@@ -125,21 +124,6 @@ static __device__ __forceinline__ void ns_fit_body(const ns_unit_src &src, const
         atomicAdd(&cnt->fast_seed, tot_seed);
         atomicAdd(&cnt->fast_lattice, tot_lat);
     }
-}
-
-/* two samples per lane in flight, 96 registers, five CTAs per SM: panels of up to 64 samples (one pair-round) */
-__global__ void __launch_bounds__(128, NS_FIT_MINB)
-k_fit(ns_unit_src src, const __grid_constant__ ns_params prm, int64_t u0, ns_unit_arrays ua, ns_counters *cnt)
-{
-    ns_fit_body<2>(src, prm, u0, ua, cnt);
-}
-
-/* four samples per lane in flight, 128 registers, four CTAs per SM: panels of more than 64 samples (n = 100: ONE round of
- * four chains instead of two pair-rounds, 16 chains per scheduler instead of 10) */
-__global__ void __launch_bounds__(128, 4)
-k_fit4(ns_unit_src src, const __grid_constant__ ns_params prm, int64_t u0, ns_unit_arrays ua, ns_counters *cnt)
-{
-    ns_fit_body<4>(src, prm, u0, ua, cnt);
 }
 
 /* One thread-block cluster per unit: the CTAs of the cluster split the unit's samples, every

@@ -78,7 +78,6 @@ static inline int ns_gate_form(int mode, int extra_rob, int64_t u0, int n, doubl
 __global__ void k_gate_staged(ns_unit_src src, ns_params prm, int64_t u0, int n_units, ns_unit_arrays ua, ns_counters *cnt,
                               int stage_k, int stages, int n_full_blocks, int lean);
 __global__ void k_fit(ns_unit_src src, const __grid_constant__ ns_params prm, int64_t u0, ns_unit_arrays ua, ns_counters *cnt);
-__global__ void k_fit4(ns_unit_src src, const __grid_constant__ ns_params prm, int64_t u0, ns_unit_arrays ua, ns_counters *cnt);
 __global__ void k_fit_heavy(ns_unit_src src, const __grid_constant__ ns_params prm, int64_t u0, ns_unit_arrays ua, ns_counters *cnt,
                             int which, int *started);
 __global__ void k_fit_heavy_tp(ns_unit_src src, const __grid_constant__ ns_params prm, int64_t u0, ns_unit_arrays ua, ns_counters *cnt,

@@ -53,9 +53,7 @@ int emul_unit(int n, const int32_t *dp, const int32_t *vp, const int32_t *vm, co
             w.x[i] = keep ? x : 0.0;
         }
         ns_fit_result res;
-        if (fast == 2)
-            ns_fit_unit<SerialG, 1, 4>(w, n, maxmu, prm, res); /* the four-chain form of k_fit4 */
-        else if (fast)
+        if (fast)
             ns_fit_unit<SerialG, 1>(w, n, maxmu, prm, res);
         if (!fast || res.deferred) { /* the warp kernel hands such units to the heavy kernel */
             for (int i = 0; i < n; i++) {
