@@ -367,7 +367,9 @@ def strong_one(a, cfg, P, n, config, ns, prm, h_ref, h_counts, ng, check=True):
         same = bool(R1.n_emitted == R.n_emitted and R1.n_fitted == R.n_fitted and np.array_equal(R1.emit_unit, R.emit_unit)
                     and np.array_equal(R1.gq, R.gq, equal_nan=True) and np.array_equal(R1.sigma, R.sigma, equal_nan=True))
     config = dict(config, parallelism=f"one host process, {ng} devices, queue of position chunks (ns_multi_call_snv)",
-                  positions_total=P)
+                  positions_total=P,
+                  workload=f"{cfg.name}: {n} samples x {P} positions IN TOTAL at ~{cfg.depth:g}X, SNV alleles (3 per position), "
+                           f"one table split over {ng} GPU(s)")
     config.pop("positions_per_gpu", None)
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": ng, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
