@@ -603,6 +603,7 @@ def main():
             Rh = step_host()
             fitted_h += Rh.n_fitted
         e1.record()
+        tm_h = caller.timings()
         barrier()
         ms_h_own = e0.elapsed_time(e1)
         ms_h = allmax(ms_h_own)
@@ -612,6 +613,7 @@ def main():
         e2e = {"value": allsum(fitted_h) / (ms_h * 1e-3), "unit": UNIT,
                "h2d_bytes_per_step": int(h_counts.nbytes + h_ref.nbytes), "d2h_bytes_per_step": int(d2h),
                "ms_per_step": ms_h / a.steps, "per_rank_ms": per_rank_ms_e2e,
+               "kernel_ms_last_call_rank0": {k: v for k, v in tm_h.items() if k.endswith("_ms")},
                "api": "needlestack_b200.Caller.call_snv -> ns_call_snv (C ABI)" + (", emitted rows only" if a.rows_only else "")}
         assert Rh.n_fitted == R.n_fitted and Rh.n_emitted == R.n_emitted
         ref_np = h_ref.array[: min(P, REF_SAMPLE_POSITIONS)].copy()

@@ -686,12 +686,15 @@ static int ns_pool_submit(ns_ctx *ctx, const ns_params &dprm, const ns_unit_src 
     const char *emc = getenv("NS_POOL_MAX_CLUSTERS");
     if (emc && atoi(emc) > 0)
         max_cl = atoi(emc);
-    /* Earlier pool launches still running (streaming shapes: a chunk takes less time than one cluster-path unit): the new
-     * clusters could not become resident whatever the host does, and waiting for them would only stall the chunk */
+    /* Earlier pool launches still running: their clusters hold SMs, the new ones may or may not find room at once.
+     * Streaming shapes (a chunk takes less time than one cluster-path unit) must not stall on that, but where a chunk
+     * and a unit take about as long (n = 400) skipping the wait lets the warp kernel take every SM first and pushes the
+     * unit behind it, chunk after chunk (C4 end to end: 190 ms of tail): wait, but only briefly. */
+    double wait_cap = 0.005;
     if (wait_resident)
         for (int i = 0; i < NS_POOL_STREAMS; i++)
             if (pl.used[i] && pl.n_launch > 0 && cudaEventQuery(pl.ev_t1[i]) == cudaErrorNotReady)
-                wait_resident = false;
+                wait_cap = 0.0005;
     cudaGetLastError();
     int *started = wait_resident ? ctx->d_started : nullptr;
     if (wait_resident)
@@ -706,7 +709,7 @@ static int ns_pool_submit(ns_ctx *ctx, const ns_params &dprm, const ns_unit_src 
          * wait on a mapped flag until the clusters are resident (not a kernel waiting on a kernel) */
         const auto t0 = std::chrono::steady_clock::now();
         while (*(volatile int *)ctx->h_started < ncl) {
-            if (std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() > 0.005)
+            if (std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() > wait_cap)
                 break;
         }
     }
