@@ -1198,21 +1198,29 @@ static int ns_run_chunk(ns_ctx *ctx, const ns_params &dprm, const double *qtab, 
     return NS_OK;
 }
 
-int64_t ns_pick_chunk(ns_ctx *ctx, int n, int64_t total_units)
+int64_t ns_pick_chunk(ns_ctx *ctx, int n, int64_t total_units, bool device_resident)
 {
     int64_t c;
     if (ctx->chunk_units > 0) {
         c = ctx->chunk_units;
     } else {
-        /* bound the per-chunk result planes (58 B per sample per row, twice with the packed copy): <= ~6 GB */
-        c = (int64_t)(6000.0e6 / (58.0 * n));
-        /* ~1 GB of count planes per chunk, at least 262144 positions: small panels (WGS-like, few samples) get
-         * proportionally more positions per chunk */
-        int64_t cap = 3 * (int64_t)(0.94e9 / (36.0 * n)); /* n = 100: 262144 positions, the measured end-to-end optimum */
+        /* Device-resident planes of small panels (WGS-like: almost every unit is gated, the chunk is a streaming pass with
+         * a handful of cluster-path units): nothing to overlap with a copy, so chunks four times as large - the
+         * cluster-path units of a chunk start when its gate has run, and fewer, larger chunks start them earlier (C5, 4 M
+         * positions: 8 chunks 47 ms per step, 2 chunks 39.5 ms).  Not for
+         * larger panels: at n = 100 a chunk's 25 such units already hold every SM for its first ~35 ms. */
+        const bool big = device_resident && n <= 64;
+        /* bound the per-chunk result planes (58 B per sample per row, twice with the packed copy): <= ~6 GB if every unit
+         * were fitted (small panels: a fraction of a percent is) */
+        c = (int64_t)((big ? 24000.0e6 : 6000.0e6) / (58.0 * n));
+        /* ~1 GB of count planes per chunk, at least 262144 positions (the chunk is the unit of the H2D / compute
+         * overlap: n = 100: 262144 positions, the measured end-to-end optimum; small panels get proportionally more
+         * positions per chunk) */
+        int64_t cap = 3 * (int64_t)((big ? 3.76e9 : 0.94e9) / (36.0 * n));
         if (cap < 3 * 262144)
             cap = 3 * 262144;
-        if (cap > 3 * 2097152)
-            cap = 3 * 2097152; /* per-unit arrays: ~70 B per unit */
+        if (cap > 3 * (big ? 4194304 : 2097152))
+            cap = 3 * (big ? 4194304 : 2097152); /* per-unit arrays: ~70 B per unit */
         if (c > cap)
             c = cap;
         if (c < 3 * 256)
@@ -1291,7 +1299,7 @@ static int ns_snv_device_body(ns_ctx *ctx, const ns_params *prm, int n, int64_t 
     cudaEvent_t t0 = ctx->ev[8], t1 = ctx->ev[9];
     CK(cudaEventRecord(t0, ctx->stream));
     const int64_t U = 3 * P;
-    const int64_t chunk = U > 0 ? ns_pick_chunk(ctx, n, U) : 0;
+    const int64_t chunk = U > 0 ? ns_pick_chunk(ctx, n, U, true) : 0;
     int64_t emit_off = 0;
     RowSink sink = ns_sink_from_out(out);
     ns_unit_src src;

@@ -164,7 +164,7 @@ struct ns_ctx {
 
 /* ---- shared between ns_api.cu and ns_multi.cu ---- */
 int ns_prepare_params(ns_ctx *ctx, const ns_params *in, int n, ns_params *dprm, const double **qtab);
-int64_t ns_pick_chunk(ns_ctx *ctx, int n, int64_t total_units);
+int64_t ns_pick_chunk(ns_ctx *ctx, int n, int64_t total_units, bool device_resident = false);
 void ns_reset_out(ns_ctx *ctx, ns_out *out);
 void ns_drain(ns_ctx *ctx);
 RowSink ns_sink_from_out(ns_out *out);

@@ -101,10 +101,17 @@ static int ns_multi_snv(ns_multi *m, const ns_params *prm, int n, int64_t P, con
     }
     const int64_t U = 3 * P;
     ChunkQueue q;
-    /* chunk size: what one device would take, but at least ~4 chunks per device so that the queue can balance,
-     * and not below 16384 positions (per-chunk fixed costs: two host round trips and ~10 small launches) */
+    /* Chunk size.  A device's cluster-path units start when the gate of their chunk has run and take 35-130 ms each
+     * whatever else the device does: when a device's whole share is of that order (a 1 Mb panel over 8 GPUs: ~45 ms
+     * of fits per device) the share must be ONE chunk, so that they all start at once - with four chunks the units of
+     * the last one start after three quarters of the work and the device ends up waiting for them (measured: 106 ms
+     * against 7x ms).  Larger shares are cut finer, so that the queue can balance the data-dependent work: 2 chunks
+     * per device up to ~300 ms of estimated share, 4 beyond; never more than one device would take at a time, never
+     * fewer than 16384 positions.  Estimate: ~4 ns per sample and position (C2 3.5, C4 6.3). */
     int64_t pc = U > 0 ? ns_pick_chunk(m->ctx[0], n, U) / 3 : 1;
-    int64_t per = (P + (int64_t)D * 4 - 1) / ((int64_t)D * 4);
+    const double share_ms = 4.0e-6 * (double)n * (double)P / (double)D;
+    const int pieces = share_ms < 100.0 ? 1 : (share_ms < 300.0 ? 2 : 4);
+    int64_t per = (P + (int64_t)D * pieces - 1) / ((int64_t)D * pieces);
     if (per < 16384)
         per = 16384;
     if (pc > per)
