@@ -49,6 +49,8 @@ def parse():
     ap.add_argument("--rows-only", action="store_true",
                     help="end-to-end leg asks for the emitted rows only (per-unit output pointers NULL: no per-unit D2H)")
     ap.add_argument("--no-text", action="store_true", help="skip the text-table leg (loader and drop-in driver timings)")
+    ap.add_argument("--text-tile", type=int, default=48, help="text-table leg: the 16000 distinct synthetic positions are "
+                    "tiled this many times (48: 768000 positions x 100 samples, 2.1 GB of text)")
     ap.add_argument("--p-germline", type=float, default=1e-4)
     ap.add_argument("--dump-cycles", default="")
     ap.add_argument("--gpus-list", default="", help="--scaling strong: comma-separated device counts to run on the SAME "
@@ -654,7 +656,7 @@ def main():
     text = None
     if rank == 0 and world == 1 and not a.no_text and not a.no_cpu:
         try:
-            text = text_leg(cfg, local_rank)
+            text = text_leg(cfg, local_rank, tile=max(a.text_tile, 1))
         except Exception as e:  # the headline does not depend on this leg
             text = {"error": repr(e)[:300]}
     if rank == 0:

@@ -1369,9 +1369,13 @@ int ns_snv_host_queue(ns_ctx *ctx, const ns_params *prm, int n, int64_t P, const
         CK(cudaEventRecord(ctx->ev_h2d[buf], ctx->copy_stream));
         return NS_OK;
     };
+    int64_t taken = 0;
     auto take = [&]() -> int64_t {
-        if (q->failed.load())
+        /* max_per_slot: the queue prefetches one chunk ahead, so with as many chunks as devices the threads that
+         * start first would take two each and leave the last devices idle */
+        if (q->failed.load() || (q->max_per_slot > 0 && taken >= q->max_per_slot))
             return -1;
+        taken++;
         const int64_t ci = q->next.fetch_add(1);
         if (ci >= q->n_chunks)
             return -1;

@@ -119,6 +119,7 @@ struct RowSink {
 struct ChunkQueue {
     std::atomic<int64_t> next{0};
     int64_t n_chunks = 0, pchunk = 0;
+    int64_t max_per_slot = 0;    /* most chunks one device may take (0: no limit) */
     std::atomic<int> failed{0};
     std::vector<int> owner;      /* device slot that took chunk c (multi-GPU calls; empty otherwise) */
 };

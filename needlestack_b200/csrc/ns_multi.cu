@@ -102,15 +102,19 @@ static int ns_multi_snv(ns_multi *m, const ns_params *prm, int n, int64_t P, con
     const int64_t U = 3 * P;
     ChunkQueue q;
     /* Chunk size.  A device's cluster-path units start when the gate of their chunk has run and take 35-130 ms each
-     * whatever else the device does: when a device's whole share is of that order (a 1 Mb panel over 8 GPUs: ~45 ms
-     * of fits per device) the share must be ONE chunk, so that they all start at once - with four chunks the units of
-     * the last one start after three quarters of the work and the device ends up waiting for them (measured: 106 ms
-     * against 7x ms).  Larger shares are cut finer, so that the queue can balance the data-dependent work: 2 chunks
-     * per device up to ~300 ms of estimated share, 4 beyond; never more than one device would take at a time, never
-     * fewer than 16384 positions.  Estimate: ~4 ns per sample and position (C2 3.5, C4 6.3). */
+     * whatever else the device does, so when a device's whole share is of that order (a 1 Mb panel over 8 GPUs: ~45 ms
+     * of fits per device) many small chunks make the device wait for the units of its last chunk.  Measured, C2 over
+     * 8 GPUs: 4 chunks per device 105 ms, 2 chunks 95-97 ms, 1 chunk 102 ms (no copy/compute overlap); over 4 GPUs:
+     * 2 chunks 125 ms, 1 chunk 127 ms.  The floor is the slowest single unit (~90 ms on the device that gets it).
+     * So: 2 chunks per device up to ~300 ms of estimated share, dealt evenly; 4 beyond, first come first served,
+     * so that the queue balances the data-dependent work; never fewer than 16384 positions.
+     * Estimate: ~4 ns per sample and position (C2 3.5, C4 6.3). */
     int64_t pc = U > 0 ? ns_pick_chunk(m->ctx[0], n, U) / 3 : 1;
     const double share_ms = 4.0e-6 * (double)n * (double)P / (double)D;
-    const int pieces = share_ms < 100.0 ? 1 : (share_ms < 300.0 ? 2 : 4);
+    int pieces = share_ms < 300.0 ? 2 : 4;
+    const char *ep = getenv("NS_MULTI_PIECES");
+    if (ep && atoi(ep) > 0)
+        pieces = atoi(ep);
     int64_t per = (P + (int64_t)D * pieces - 1) / ((int64_t)D * pieces);
     if (per < 16384)
         per = 16384;
@@ -124,6 +128,9 @@ static int ns_multi_snv(ns_multi *m, const ns_params *prm, int n, int64_t P, con
     q.pchunk = pc;
     q.n_chunks = P > 0 ? (P + pc - 1) / pc : 0;
     q.owner.assign((size_t)q.n_chunks, -1);
+    /* few chunks per device: an even deal (every thread prefetches one chunk ahead, so the threads that start first
+     * would otherwise take the chunks of the last ones); many: first come, first served, which balances the work */
+    q.max_per_slot = pieces <= 2 ? (q.n_chunks + D - 1) / D : 0;
     const RowSink proto = ns_sink_from_out(out);
     std::vector<ns_out> o((size_t)D, *out);
     std::vector<RowSink> sink((size_t)D);
