@@ -324,12 +324,13 @@ struct ns_cspline_fn {
     __device__ __forceinline__ double operator()(double u) const { return ns_cspline_eval(*s, u); }
 };
 
+template <bool ROLLED>
 __device__ __forceinline__ double ns_cintegrate(const ns_cspline &s, int &ier, int &npanels)
 {
     const double tol = 1.220703125e-4; /* .Machine$double.eps^0.25 */
     ns_cspline_fn f = {&s};
     ns_quad_out q;
-    ns_dqagse_t<ns_k21_coop>(f, s.j1, s.j2 + 1.0, tol, tol, q);
+    ns_dqagse_t<ns_k21_coop, ns_cspline_fn, ROLLED>(f, s.j1, s.j2 + 1.0, tol, tol, q);
     ier = q.ier;
     npanels += q.neval / 21;
     return q.result;
@@ -349,6 +350,7 @@ __device__ __forceinline__ void ns_lane_block(int n, int &k0, int &k1)
 }
 
 /* ai.sig.tukey(mui, sig, c), glm_rob_nb.r:141-160, one sample per warp */
+template <bool ROLLED>
 static __device__ __noinline__ double ns_ai_coop(double mui, double sig, double c, int n_ai, double dg0,
                                           const ns_coop_scratch &sc, ns_fit_counters &cnt)
 {
@@ -372,8 +374,8 @@ static __device__ __noinline__ double ns_ai_coop(double mui, double sig, double 
         const double b = fmin(j2, a + per - 1);
         double acc = 0;
         if (a <= j2) {
-            double pm = ns_dnbinom_mu(a, invsig, mui);
-            double D = (a == 0) ? 0.0 : ns_digamma(a + invsig) - dg0;
+            double pm = ns_dnbinom_mu_c(a, invsig, mui);
+            double D = (a == 0) ? 0.0 : ns_digamma_c(a + invsig) - dg0;
             for (double j = a; j <= b; j += 1) {
                 double d = j - mui;
                 double t = d * inv_csd;
@@ -396,10 +398,10 @@ static __device__ __noinline__ double ns_ai_coop(double mui, double sig, double 
             /* pmf by recurrence along the lattice (1/(j+1) from the table), the digamma
              * difference directly at each knot */
             double j = ns_cknot(j1, j2, by, n_ai, k0);
-            double pm = ns_dnbinom_mu(j, invsig, mui);
+            double pm = ns_dnbinom_mu_c(j, invsig, mui);
             /* digamma(j + 1/sig) - digamma(1/sig): one evaluation at the lane's first knot, then the recurrence
              * digamma(x + 1) = digamma(x) + 1/x along the walk (a digamma per knot cost more than the <= 16 steps) */
-            double D = (j == 0) ? 0.0 : ns_digamma(j + invsig) - dg0;
+            double D = (j == 0) ? 0.0 : ns_digamma_c(j + invsig) - dg0;
             int k = k0;
             double xk = j;
             for (;; j += 1) {
@@ -420,8 +422,8 @@ static __device__ __noinline__ double ns_ai_coop(double mui, double sig, double 
                 double j = ns_cknot(j1, j2, by, n_ai, k);
                 double t = (j - mui) * inv_csd;
                 double w = (t * t - 1) * (t * t - 1);
-                double psi = ns_digamma(j + invsig) - dg0 - lg - (j - mui) * inv_mpi;
-                sc.y[k] = w * psi * ns_dnbinom_mu(j, invsig, mui);
+                double psi = ns_digamma_c(j + invsig) - dg0 - lg - (j - mui) * inv_mpi;
+                sc.y[k] = w * psi * ns_dnbinom_mu_c(j, invsig, mui);
             }
         }
     }
@@ -435,7 +437,7 @@ static __device__ __noinline__ double ns_ai_coop(double mui, double sig, double 
     ns_cspline_coefs(sc, n_ai, j1, j2, by);
     ns_cspline s = {n_ai, j1, j2, by, 1.0 / by, sc.y, sc.c, sc.rt, sc.rtn, sc.ib, sc.m};
     int ier = 0, np = 0;
-    double v = ns_cintegrate(s, ier, np);
+    double v = ns_cintegrate<ROLLED>(s, ier, np);
     cnt.n_quad += (unsigned long long)np;
     if (ier == 7)
         cnt.quad_overflow = 1;
@@ -446,6 +448,7 @@ static __device__ __noinline__ double ns_ai_coop(double mui, double sig, double 
 }
 
 /* E.tukeypsi.1 / E.tukeypsi.2 (glm_rob_nb.r:109-140), one sample per warp */
+template <bool ROLLED>
 static __device__ __noinline__ void ns_E12_coop(double mui, double sig, double c, int n_ai, const ns_coop_scratch &sc,
                                          ns_fit_counters &cnt, double *e1, double *e2)
 {
@@ -470,7 +473,7 @@ static __device__ __noinline__ void ns_E12_coop(double mui, double sig, double c
         const double b = fmin(j2, a + per - 1);
         double a1 = 0, a2 = 0;
         if (a <= j2) {
-            double pm = ns_dnbinom_mu(a, size, mui);
+            double pm = ns_dnbinom_mu_c(a, size, mui);
             for (double j = a; j <= b; j += 1) {
                 double d = j - mui;
                 double t = d * inv_csd;
@@ -493,7 +496,7 @@ static __device__ __noinline__ void ns_E12_coop(double mui, double sig, double c
     if (k0 < k1) {
         if (by <= NS_STEP_BY) {
             double j = ns_cknot(j1, j2, by, n_ai, k0);
-            double pm = ns_dnbinom_mu(j, size, mui);
+            double pm = ns_dnbinom_mu_c(j, size, mui);
             int k = k0;
             double xk = j;
             for (;; j += 1) {
@@ -512,27 +515,39 @@ static __device__ __noinline__ void ns_E12_coop(double mui, double sig, double c
                 double j = ns_cknot(j1, j2, by, n_ai, k);
                 double t = (j - mui) * inv_csd;
                 double w = (t * t - 1) * (t * t - 1);
-                sc.y[k] = w * (j - mui) * ns_dnbinom_mu(j, size, mui);
+                sc.y[k] = w * (j - mui) * ns_dnbinom_mu_c(j, size, mui);
             }
         }
     }
     __syncwarp();
     ns_cpiv P;
     ns_cspline_pivots(P, n_ai, j1, j2, by);
-    ns_cspline_solve(P, sc, n_ai);
-    __syncwarp();
-    ns_cspline_coefs(sc, n_ai, j1, j2, by);
     ns_cspline s = {n_ai, j1, j2, by, 1.0 / by, sc.y, sc.c, sc.rt, sc.rtn, sc.ib, sc.m};
     int ier1 = 0, ier2 = 0, np = 0;
-    double v1 = ns_cintegrate(s, ier1, np);
-    __syncwarp();
-    for (int k = k0; k < k1; k++)
-        sc.y[k] *= (ns_cknot(j1, j2, by, n_ai, k) - mui); /* w*(j-mu)^2*pmf */
-    __syncwarp();
-    ns_cspline_solve(P, sc, n_ai);
-    __syncwarp();
-    ns_cspline_coefs(sc, n_ai, j1, j2, by);
-    double v2 = ns_cintegrate(s, ier2, np);
+    double v1 = 0, v2 = 0;
+    /* the two integrals share one copy of the solve + dqags code (a rolled loop: the kernel is bound by instruction
+     * fetch where many warps are in different phases) */
+#pragma unroll 1
+    for (int pass = 0; pass < 2; pass++) {
+        if (pass == 1) {
+            for (int k = k0; k < k1; k++)
+                sc.y[k] *= (ns_cknot(j1, j2, by, n_ai, k) - mui); /* w*(j-mu)^2*pmf */
+            __syncwarp();
+        }
+        ns_cspline_solve(P, sc, n_ai);
+        __syncwarp();
+        ns_cspline_coefs(sc, n_ai, j1, j2, by);
+        int ier = 0;
+        const double v = ns_cintegrate<ROLLED>(s, ier, np);
+        __syncwarp();
+        if (pass == 0) {
+            v1 = v;
+            ier1 = ier;
+        } else {
+            v2 = v;
+            ier2 = ier;
+        }
+    }
     cnt.n_quad += (unsigned long long)np;
     if (ier1 == 7 || ier2 == 7)
         cnt.quad_overflow = 1;

@@ -20,6 +20,7 @@
 /* ---- lane groups ----------------------------------------------------------------- */
 #if defined(__CUDACC__)
 struct WarpG {
+    static constexpr bool rolled = false; /* see ns_dqagse_t */
     __device__ static __forceinline__ int nl() { return 32; }
     __device__ static __forceinline__ int lane() { return threadIdx.x & 31; }
     __device__ static __forceinline__ double sum(double v)
@@ -109,6 +110,7 @@ struct WarpG {
 /* one CTA = one unit, one WARP = one "lane" of the group (the heavy kernel): the values handed to
  * the collectives are uniform across each warp; reductions go through shared memory */
 struct CoopG {
+    static constexpr bool rolled = false; /* see ns_dqagse_t */
     __device__ static __forceinline__ int nl() { return blockDim.x >> 5; }
     __device__ static __forceinline__ int lane() { return threadIdx.x >> 5; }
     __device__ static __forceinline__ double *red()
@@ -161,6 +163,7 @@ struct CoopG {
  * (cluster.map_shared_rank) with one barrier.cluster per reduction (double-buffered slots).
  * Values handed to the collectives are uniform within each warp. */
 struct ClusterG {
+    static constexpr bool rolled = false; /* see ns_dqagse_t */
     __device__ static __forceinline__ unsigned crank()
     {
         unsigned r;
@@ -239,8 +242,14 @@ struct ClusterG {
     __device__ static __forceinline__ void fill_r2tab(double *, const double *, double, int) {}
 };
 
+/* the same for the throughput form of the kernel (k_fit_heavy_tp): smaller code where it costs latency (ns_dqagse_t) */
+struct ClusterGT : ClusterG {
+    static constexpr bool rolled = true;
+};
+
 /* one CTA = one unit (the heavy kernel): reductions through shared memory */
 struct BlockG {
+    static constexpr bool rolled = false; /* see ns_dqagse_t */
     __device__ static __forceinline__ int nl() { return blockDim.x; }
     __device__ static __forceinline__ int lane() { return threadIdx.x; }
     __device__ static __forceinline__ double *red() 
@@ -294,6 +303,7 @@ struct BlockG {
 #endif
 
 struct SerialG {
+    static constexpr bool rolled = false; /* see ns_dqagse_t */
     static NS_HD int nl() { return 1; }
     static NS_HD int lane() { return 0; }
     static NS_HD double sum(double v) { return v; }

@@ -66,16 +66,43 @@ NS_HD double ns_tukeypsi(double r, double c)
     return t * t * r;
 }
 
+/* One copy each of the large scalar functions for the whole cluster kernel (k_fit keeps them inlined).  Force-inlined
+ * they made ns_ai_coop and ns_E12_coop 237 KB and 296 KB of code (three copies of dnbinom_mu with its lgamma /
+ * stirlerr / bd0 each, three of dqags) against 32 KB of instruction cache per SM: with the 16-20 warps of a CTA in
+ * different phases of different samples, 44 % of the stall samples of the throughput regime (C3) were instruction
+ * fetches.  OOL = true selects the shared copy. */
+#if defined(__CUDACC__)
+static __device__ __noinline__ double ns_dnbinom_mu_c(double x, double size, double mu) { return ns_dnbinom_mu(x, size, mu); }
+static __device__ __noinline__ double ns_digamma_c(double x) { return ns_digamma(x); }
+#endif
+template <bool OOL> NS_GF inline double ns_pmf_seed(double x, double size, double mu)
+{
+#if defined(__CUDA_ARCH__)
+    if (OOL)
+        return ns_dnbinom_mu_c(x, size, mu);
+#endif
+    return ns_dnbinom_mu(x, size, mu);
+}
+template <bool OOL> NS_GF inline double ns_digamma_sel(double x)
+{
+#if defined(__CUDA_ARCH__)
+    if (OOL)
+        return ns_digamma_c(x);
+#endif
+    return ns_digamma(x);
+}
+
 /* ---- generic window expectations ----------------------------------------------------- */
 /* lattice-sum branch of ai.sig.tukey (glm_rob_nb.r:155-158) */
+template <bool OOL = false>
 NS_GF inline double ns_ai_sum(double mui, double sig, double c, double j1, double j2, double dg0)
 {
     const double sqrtV = sqrt(mui * (sig * mui + 1));
     const double invsig = 1 / sig;
     const double lg = log(mui / invsig + 1);
     const double csd = c * sqrtV, mpi = mui + invsig;
-    double pm = ns_dnbinom_mu(j1, invsig, mui);
-    double D = (j1 == 0) ? 0.0 : ns_digamma(j1 + invsig) - dg0; /* digamma(j+1/sig)-digamma(1/sig) */
+    double pm = ns_pmf_seed<OOL>(j1, invsig, mui);
+    double D = (j1 == 0) ? 0.0 : ns_digamma_sel<OOL>(j1 + invsig) - dg0; /* digamma(j+1/sig)-digamma(1/sig) */
     const double q = mui / (mui + invsig);
     const double inv_csd = 1.0 / csd, inv_mpi = 1.0 / mpi; /* the loop itself is division-free */
     double acc = 0;
@@ -161,11 +188,12 @@ NS_GF inline double ns_ai_sig_tukey(double mui, double sig, double c, int n_ai, 
 }
 
 /* lattice-sum branch of E.tukeypsi.1 / .2 (glm_rob_nb.r:119-122, 135-138), both in one pass */
+template <bool OOL = false>
 NS_GF inline void ns_E12_sum(double mui, double sig, double c, double j1, double j2, double &e1, double &e2)
 {
     const double sqrtV = sqrt(ns_varfunc(mui, sig));
     const double size = 1 / sig, csd = c * sqrtV;
-    double pm = ns_dnbinom_mu(j1, size, mui);
+    double pm = ns_pmf_seed<OOL>(j1, size, mui);
     const double q = mui / (mui + size);
     const double inv_csd = 1.0 / csd;
     double a1 = 0, a2 = 0;
@@ -257,8 +285,10 @@ struct ns_coop_scratch {
     int rtn;
 };
 #if defined(__CUDACC__)
+template <bool ROLLED>
 static __device__ __noinline__ double ns_ai_coop(double mui, double sig, double c, int n_ai, double dg0,
                                                  const ns_coop_scratch &sc, ns_fit_counters &cnt);
+template <bool ROLLED>
 static __device__ __noinline__ void ns_E12_coop(double mui, double sig, double c, int n_ai, const ns_coop_scratch &sc,
                                                 ns_fit_counters &cnt, double *e1, double *e2);
 #endif
@@ -526,7 +556,7 @@ NS_GFN double ns_sig_objective(double sig, const ns_work &w, int n, const ns_par
         cnt.n_seed += n_seed;
         cnt.n_lattice += n_lat;
     } else {
-        const double dg0 = ns_digamma(invsig);
+        const double dg0 = ns_digamma_sel<MODE == 2>(invsig);
         const double twon = (double)(2 * prm.n_ai_sig_tukey);
 #if defined(__CUDA_ARCH__)
         /* throughput regime only: with few samples per warp (a unit on a full cluster) the lanes sharing one
@@ -560,14 +590,14 @@ NS_GFN double ns_sig_objective(double sig, const ns_work &w, int n, const ns_par
                 const double wi = ns_tukeypsi(r, c) / r;
                 double term = 0.0;
                 if (wi != 0.0) {
-                    double psiML = ns_digamma(r * sqrt(mu * (sig * mu + 1)) + mu + 1 / sig) -
+                    double psiML = ns_digamma_sel<true>(r * sqrt(mu * (sig * mu + 1)) + mu + 1 / sig) -
                                    sig * r * sqrt(mu / (sig * mu + 1)) - dg0 - log(sig * mu + 1);
                     term = wi * psiML;
                 }
                 nsA++;
                 if (!(j1 > j2)) {
                     nlA += (int)(j2 - j1 + 1);
-                    term -= ns_ai_sum(mu, sig, c, j1, j2, dg0);
+                    term -= ns_ai_sum<true>(mu, sig, c, j1, j2, dg0);
                 }
                 accA += term;
             }
@@ -604,7 +634,7 @@ NS_GFN double ns_sig_objective(double sig, const ns_work &w, int n, const ns_par
             if (wi == 0.0) {
                 term = 0.0; /* 0 * finite psi.sig.ML */
             } else {
-                double psiML = ns_digamma(r * sqrt(mu * (sig * mu + 1)) + mu + 1 / sig) -
+                double psiML = ns_digamma_sel<MODE == 2>(r * sqrt(mu * (sig * mu + 1)) + mu + 1 / sig) -
                                sig * r * sqrt(mu / (sig * mu + 1)) - dg0 - log(sig * mu + 1);
                 term = wi * psiML;
             }
@@ -612,7 +642,7 @@ NS_GFN double ns_sig_objective(double sig, const ns_work &w, int n, const ns_par
             cnt.quad_err = 0;
 #if defined(__CUDA_ARCH__)
             if (MODE == 2)
-                term -= ns_ai_coop(mu, sig, c, prm.n_ai_sig_tukey, dg0, w.coop, cnt);
+                term -= ns_ai_coop<G::rolled>(mu, sig, c, prm.n_ai_sig_tukey, dg0, w.coop, cnt);
             else
 #endif
                 term -= ns_ai_sig_tukey(mu, sig, c, prm.n_ai_sig_tukey, dg0, cnt);
@@ -835,7 +865,7 @@ NS_GFN double ns_irls_step(double sig, const ns_work &w, int n, double maxmu, co
                 nsA++;
                 if (!(j1 > j2)) {
                     nlA += (int)(j2 - j1 + 1);
-                    ns_E12_sum(mu, sig, c, j1, j2, e1, sap);
+                    ns_E12_sum<true>(mu, sig, c, j1, j2, e1, sap);
                 }
                 const double ee = exp(eta);
                 const double bi = sap * (1.0 / (V * sV)) * (ee * ee);
@@ -885,7 +915,7 @@ NS_GFN double ns_irls_step(double sig, const ns_work &w, int n, double maxmu, co
             const double sV = sqrt(V);
 #if defined(__CUDA_ARCH__)
             if (MODE == 2) {
-                ns_E12_coop(mu, sig, c, prm.n_ai_sig_tukey, w.coop, res.cnt, &e1, &sap);
+                ns_E12_coop<G::rolled>(mu, sig, c, prm.n_ai_sig_tukey, w.coop, res.cnt, &e1, &sap);
             } else
 #endif
                 ns_E_tukeypsi_12(mu, sig, c, prm.n_ai_sig_tukey, res.cnt, e1, sap);

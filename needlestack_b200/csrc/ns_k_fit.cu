@@ -132,6 +132,7 @@ k_fit(ns_unit_src src, const __grid_constant__ ns_params prm, int64_t u0, ns_uni
 #ifndef NS_HEAVY_MINB
 #define NS_HEAVY_MINB 1 /* 128 registers; 64 (to leave half the register file to the warp kernel) spills and is 1.8x slower */
 #endif
+template <class CG>
 static __device__ __forceinline__ void ns_fit_heavy_body(const ns_unit_src &src, const ns_params &prm, int64_t u0,
                                                          const ns_unit_arrays &ua, ns_counters *cnt, int which, int *started)
 {
@@ -185,7 +186,7 @@ static __device__ __forceinline__ void ns_fit_heavy_body(const ns_unit_src &src,
         maxmu = BlockG::max(maxmu);
         __syncthreads();
         ns_fit_result res;
-        ns_fit_unit<ClusterG, 2>(w, n, maxmu, prm, res);
+        ns_fit_unit<CG, 2>(w, n, maxmu, prm, res);
         if (lane == 0) { /* counters are uniform within a warp, disjoint across warps and CTAs */
             tot_seed += res.cnt.n_seed;
             tot_lat += res.cnt.n_lattice;
@@ -208,12 +209,12 @@ static __device__ __forceinline__ void ns_fit_heavy_body(const ns_unit_src &src,
 __global__ void __launch_bounds__(NS_HEAVY_THREADS, NS_HEAVY_MINB)
 k_fit_heavy(ns_unit_src src, const __grid_constant__ ns_params prm, int64_t u0, ns_unit_arrays ua, ns_counters *cnt, int which, int *started)
 {
-    ns_fit_heavy_body(src, prm, u0, ua, cnt, which, started);
+    ns_fit_heavy_body<ClusterG>(src, prm, u0, ua, cnt, which, started);
 }
 
 /* throughput form, for deep panels with thousands of queued units: 20 warps per CTA at 96 registers (C3 +10 %) */
 __global__ void __launch_bounds__(NS_HEAVY_THREADS_TP, 1)
 k_fit_heavy_tp(ns_unit_src src, const __grid_constant__ ns_params prm, int64_t u0, ns_unit_arrays ua, ns_counters *cnt, int which, int *started)
 {
-    ns_fit_heavy_body(src, prm, u0, ua, cnt, which, started);
+    ns_fit_heavy_body<ClusterGT>(src, prm, u0, ua, cnt, which, started);
 }
