@@ -18,6 +18,7 @@ owns its own 1 Mb region (different seed), no data-path collective.
 """
 import argparse
 import json
+import shutil
 import os
 import subprocess
 import sys
@@ -433,7 +434,8 @@ def main():
                 "cpu_baseline": {"value": val, "unit": UNIT, "cores": ncores, "kind": "port",
                                  "sample": f"{res['positions']} positions ({res['fitted']} fitted site-alleles) "
                                            f"per step = the first positions of the b200 arm's rank-0 batch, C oracle (restatement of glm_rob_nb.r/needlestack.r; R "
-                                           f"absent), {ncores} pthreads"},
+                                           f"absent), {ncores} pthreads",
+                                 "rscript_on_path": shutil.which("Rscript")},
                 "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0}
         print(json.dumps(line))
