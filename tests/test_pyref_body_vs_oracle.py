@@ -114,3 +114,43 @@ def test_snv_body_with_pairs():
     assert seen["called"] >= 60, seen
     # every branch of the status table occurs
     assert seen["status"] == set(range(len(B.STATUS))) and seen["gt"] == {0, 1, 2, 3}, seen
+
+
+def test_indel_body():
+    """insertion / deletion alleles (needlestack.r:460-567, :623-730): the same body with all_DP = sum(DP) + sum(AO), the
+    output gate on SB_threshold_indel and the genotype on SB_threshold_SNV (as the reference has it, :540 / :556)"""
+    rng = np.random.default_rng(14)
+    ref, counts = synth.generate(synth.CONFIGS["C1"], P=60, seed=324)
+    sb_snv, sb_indel = 0.9, 0.3
+    prm = orc.call_params(SB_threshold_SNV=sb_snv, SB_threshold_indel=sb_indel)
+    n = counts.shape[2]
+    called = gate2_differs = 0
+    for p in range(60):
+        dp = counts[p, 0].astype(float)
+        r = int(ref[p])
+        rp, rm = counts[p, 1 + r].astype(float), counts[p, 5 + r].astype(float)
+        vp, vm = np.zeros(n), np.zeros(n)
+        for i in rng.choice(n, size=1 + int(rng.integers(0, 3)), replace=False):
+            tot = int(rng.binomial(int(dp[i]), rng.uniform(0.05, 0.6)))
+            vp[i] = int(rng.binomial(tot, rng.uniform(0.1, 0.9)))
+            vm[i] = tot - vp[i]
+        O = orc.call_unit(dp, vp, vm, rp, rm, prm, is_indel=True)
+        g = O["info"].glm
+        if g.gated:
+            continue
+        gq = O["gq"]
+        qv, _ = B.allele_body(dp, vp + vm, gq, g.sigma, g.slope)
+        assert close(qv, O["qval_minaf"])
+        if not np.sum(gq >= 50.0) > 0:
+            continue
+        A = B.strand_annotations(vp, vm, rp, rm)
+        assert close(A["sor"], O["sor"]) and close(A["rvsb"], O["rvsb"]) and close(A["fs"], O["fs"])
+        pooled = np.array(O["info"].pooled[:])
+        assert close([A["all_sor"], A["all_rvsb"], A["all_fs"]], pooled[:3])
+        assert pooled[7] == dp.sum() + (vp + vm).sum()
+        gate2 = bool(np.sum((A["sor"] <= sb_indel) & (gq >= 50.0)) > 0)
+        assert gate2 == bool(O["info"].gate2)
+        gate2_differs += gate2 != bool(np.sum((A["sor"] <= sb_snv) & (gq >= 50.0)) > 0)
+        assert np.array_equal(B.genotypes(gq, A["sor"], vp + vm, dp, qv, False, sb_threshold=sb_snv), O["gt"])
+        called += 1
+    assert called >= 30 and gate2_differs >= 3, (called, gate2_differs)
